@@ -1,0 +1,614 @@
+// sops_kernels.cuh — the SOPS chain kernels (sm_100a): one warp per (genome, size, seed) instance.
+//
+// Replaces, per instance, the reference's  init_sops_env → simulate(false) → evaluate_fitness  path:
+//   aggregation  src/SOPSCore/mod.rs:106-151, 271-290, 296-318
+//   separation   src/SOPSCore/separation.rs:100-240, 649-805, 811-843
+//   coating      src/SOPSCore/coating.rs:229-338, 439-555, 561-592
+//   locomotion   src/SOPSCore/locomotion.rs:98-255, 260-290, 344-532, 551-654, 661-706
+//
+// Design:
+//   * The lattice lives in shared memory as bit planes (one 32- or 64-bit word per padded row), the
+//     particle list as packed u16 (row+1 | (col+1) << 8), the genome as u16 acceptance thresholds.
+//   * The Markov chain is strictly sequential, but only ~0.3-8 % of proposals change the state.  The 32
+//     lanes therefore evaluate the next 32 proposals SPECULATIVELY against the current lattice; the
+//     first accepted proposal is committed, later lanes stay valid unless their read set touches the
+//     written cells, and the batch is cut at the first such conflict.  The retired sequence is
+//     exactly the sequential one.
+//   * Both RNG modes are counter based: fast = Philox2x32-10 keyed per step; verify = the WyRand
+//     double chain, whose draw count per step (2 or 3) depends on the state — resolved per batch by a
+//     warp-uniform walk over the "possible" ballots.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "sops_rng.cuh"
+
+namespace sops {
+
+enum { AGG = 0, SEP = 1, COAT = 2, LOCO = 3 };
+enum { MODE_VERIFY = 0, MODE_FAST = 1 };
+
+struct Instance {                   // 40 bytes, built on the host, sorted by cost (longest first)
+    uint64_t seed;                  // init seed (StdRng::seed_from_u64)
+    uint64_t move_seed;
+    uint64_t steps;
+    uint32_t genome;                // genome index
+    uint32_t slot;                  // output slot (instance id q = g*T + t)
+    uint32_t aux;                   // coat: element offset of this size's distance table
+    uint8_t arena, layers, coat, orient;
+};
+
+struct DevResult { uint32_t i0, i1, i2, status; };
+
+struct KParams {
+    const Instance* inst;
+    uint32_t n_inst;
+    const uint8_t* genomes;
+    uint32_t genome_len;
+    uint16_t prob[16];              // gene -> per-mille acceptance threshold
+    uint32_t* work_counter;
+    DevResult* out;
+    unsigned long long* counters;   // [0] attempts [1] possible [2] committed
+    uint32_t* dump;                 // optional final-state dump (words), dump_stride words per slot
+    uint32_t dump_stride;
+    uint32_t dump_slot0;            // first slot of this launch (dump rows are launch-relative)
+    const uint16_t* coat_dist;      // coat: per-size G*G distance tables (0xFFFF = none)
+    // per-warp shared-memory layout, in 32-bit words
+    uint32_t words_per_warp;
+    uint32_t off_p0, off_p1, off_p2, off_pos, off_thr, off_aux;
+    uint32_t plane_words, pos_words;
+};
+
+#define SOPS_LIGHT_WORDS 32u        // 64 u16 beams (a <= 30 -> 2a+1 <= 61)
+
+// ---------------------------------------------------------------------- direction tables --------
+// Directions in the reference's order (mod.rs:80-82): (-1,0) (1,0) (0,-1) (0,1) (-1,-1) (1,1).
+// A 9-bit window around a cell holds rows (r-1, r, r+1) x cols (c-1, c, c+1): bit = 3*row + col.
+// For a move s -> t = s + D[d]:  MID = common neighbours, BACK = nbrs(s) \ {t, MID},
+// FRONT = nbrs(t) \ {s, MID}.  Table word = MID(s-window) | BACK(s-window) << 9 | FRONT(t-window) << 18.
+__host__ __device__ constexpr int dir_bit(int d) {
+    return d == 0 ? 1 : d == 1 ? 7 : d == 2 ? 3 : d == 3 ? 5 : d == 4 ? 0 : 8;
+}
+__host__ __device__ constexpr int dir_adj(int d, int k) {   // the two directions 60 degrees either side of d
+    return d == 0 ? (k ? 4 : 3) : d == 4 ? (k ? 2 : 0) : d == 2 ? (k ? 1 : 4)
+         : d == 1 ? (k ? 5 : 2) : d == 5 ? (k ? 3 : 1) : (k ? 0 : 5);
+}
+constexpr uint32_t NB_MASK = 0x1ABu;                        // the six neighbours inside the window
+__host__ __device__ constexpr uint32_t dir_mid(int d) { return (1u << dir_bit(dir_adj(d, 0))) | (1u << dir_bit(dir_adj(d, 1))); }
+__host__ __device__ constexpr uint32_t dir_word(int d) {
+    return dir_mid(d) | ((NB_MASK & ~dir_mid(d) & ~(1u << dir_bit(d))) << 9) |
+           ((NB_MASK & ~dir_mid(d ^ 1) & ~(1u << dir_bit(d ^ 1))) << 18);
+}
+
+// packed position delta of direction d on (row | col << 8):  -1, +1, -256, +256, -257, +257
+__device__ __forceinline__ int dir_delta(uint32_t d) {
+    uint32_t h = d >> 1;
+    int mag = h ? (int)(255u + h) : 1;
+    return (d & 1) ? mag : -mag;
+}
+
+__device__ __forceinline__ uint32_t lowmask(uint32_t r) { return r >= 32 ? 0xffffffffu : ((1u << r) - 1u); }
+
+// ------------------------------------------------------------------------------ bit planes ------
+template <int RW> struct Plane;
+template <> struct Plane<1> {       // padded grid side <= 32: one u32 per row
+    static __device__ __forceinline__ uint32_t win(const uint32_t* p, uint32_t r, uint32_t cm1) { return (p[r] >> cm1) & 7u; }
+    static __device__ __forceinline__ uint32_t bit(const uint32_t* p, uint32_t r, uint32_t c) { return (p[r] >> c) & 1u; }
+    static __device__ __forceinline__ void flip(uint32_t* p, uint32_t r, uint32_t c) { p[r] ^= 1u << c; }
+    static __device__ __forceinline__ void atom_or(uint32_t* p, uint32_t r, uint32_t c) { atomicOr(&p[r], 1u << c); }
+};
+template <> struct Plane<2> {       // padded grid side <= 64: one u64 per row
+    static __device__ __forceinline__ uint32_t win(const uint32_t* p, uint32_t r, uint32_t cm1) {
+        uint64_t w = *reinterpret_cast<const uint64_t*>(p + 2 * r);
+        return (uint32_t)(w >> cm1) & 7u;
+    }
+    static __device__ __forceinline__ uint32_t bit(const uint32_t* p, uint32_t r, uint32_t c) { return (p[2 * r + (c >> 5)] >> (c & 31)) & 1u; }
+    static __device__ __forceinline__ void flip(uint32_t* p, uint32_t r, uint32_t c) { p[2 * r + (c >> 5)] ^= 1u << (c & 31); }
+    static __device__ __forceinline__ void atom_or(uint32_t* p, uint32_t r, uint32_t c) { atomicOr(&p[2 * r + (c >> 5)], 1u << (c & 31)); }
+};
+
+template <int RW>
+__device__ __forceinline__ uint32_t win9(const uint32_t* p, uint32_t r, uint32_t c) {
+    return Plane<RW>::win(p, r - 1, c - 1) | (Plane<RW>::win(p, r, c - 1) << 3) | (Plane<RW>::win(p, r + 1, c - 1) << 6);
+}
+
+// c adjacent-or-equal to x on the triangular lattice (packed positions)
+__device__ __forceinline__ bool adj_or_eq(uint32_t c, uint32_t x) {
+    int dr = (int)(c & 0xff) - (int)(x & 0xff);
+    int dc = (int)(c >> 8) - (int)(x >> 8);
+    return (unsigned)(dr + 1) <= 2u && (unsigned)(dc + 1) <= 2u && (unsigned)(dr - dc + 1) <= 2u;
+}
+
+// group index tables --------------------------------------------------------------------------------
+// separation.rs:205-222: (occupied c, same colour k) -> c(c+1)/2 + (c-k)
+__device__ __forceinline__ uint32_t sep_idx(uint32_t c, uint32_t k) { return ((c * (c + 1)) >> 1) + (c - k); }
+// coating.rs:302-320: nibble tables indexed by particles*4 + objects
+__device__ __forceinline__ uint32_t coat_idx3(uint32_t p, uint32_t o) { return (uint32_t)(0x0009004806573210ULL >> ((p * 4 + o) * 4)) & 15u; }
+__device__ __forceinline__ uint32_t coat_idx2(uint32_t p, uint32_t o) { return (uint32_t)(0x0000000500340210ULL >> ((p * 4 + o) * 4)) & 15u; }
+
+struct Geo {
+    uint32_t a, G, n;
+    uint32_t n3;                    // sep: particles per colour
+    uint32_t orient;                // loco
+};
+
+struct Lat {
+    uint32_t* p0; uint32_t* p1; uint32_t* p2;
+    uint16_t* pos; uint16_t* thr; uint16_t* light;
+    const uint32_t* dirtab;
+};
+
+// --- cheap half of a proposal: where does particle idx go in direction d, and may it? -----------
+// kind: 0 = blocked (nothing happens, 2 draws), 1 = move into empty, 2 = swap (sep only)
+template <int BEH, int RW>
+__device__ __forceinline__ void probe(const Lat& L, uint32_t idx, uint32_t d, uint32_t& s, uint32_t& t, uint32_t& kind) {
+    s = L.pos[idx];
+    t = (uint32_t)((int)s + dir_delta(d));
+    uint32_t tr = t & 0xff, tc = t >> 8;
+    if (BEH == SEP) {
+        uint32_t occ = Plane<RW>::bit(L.p0, tr, tc) | Plane<RW>::bit(L.p1, tr, tc);
+        uint32_t inv = Plane<RW>::bit(L.p2, tr, tc);
+        kind = occ ? 2u : (inv ? 0u : 1u);
+    } else {
+        kind = Plane<RW>::bit(L.p1, tr, tc) ^ 1u;
+    }
+}
+
+// locomotion.rs:260-290 on unpadded coordinates; light[b] = x | y << 8
+__device__ __forceinline__ int loco_beam(uint32_t o, int a, int x, int y) { return o == 1 ? 2 * x - y : o == 2 ? 2 * y - x : x + y - a; }
+__device__ __forceinline__ uint32_t loco_sense(const uint16_t* light, uint32_t o, int a, int x, int y) {
+    if (o == 1) { int b = 2 * x - y; if (b >= 0 && b <= 2 * a) return y >= (int)(light[b] >> 8); return 0; }
+    if (o == 2) { int b = 2 * y - x; if (b >= 0 && b <= 2 * a) return x >= (int)(light[b] & 0xff); return 0; }
+    int sxy = x + y; if (sxy >= a && sxy <= 3 * a) return x >= (int)(light[sxy - a] & 0xff); return 0;
+}
+
+__device__ __forceinline__ uint32_t sep_colour(const Geo& g, uint32_t idx) {   // hand-out order, separation.rs:126-146
+    return 1u + (idx >= g.n3) + (idx >= 2 * g.n3);
+}
+// 9-bit mask of window cells whose 2-bit colour equals col (col != 0 so empty cells never match)
+__device__ __forceinline__ uint32_t same_mask(uint32_t w0, uint32_t w1, uint32_t col) {
+    uint32_t m0 = (col & 1) ? 0x1ffu : 0u, m1 = (col & 2) ? 0x1ffu : 0u;
+    return ~((w0 ^ m0) | (w1 ^ m1)) & 0x1ffu;
+}
+
+// --- expensive half: acceptance threshold of a possible proposal -------------------------------------
+template <int BEH, int RW>
+__device__ __forceinline__ uint32_t threshold(const Lat& L, const Geo& g, uint32_t idx, uint32_t d,
+                                              uint32_t s, uint32_t t, uint32_t kind, bool& noop) {
+    uint32_t sr = s & 0xff, sc = s >> 8, tr = t & 0xff, tc = t >> 8;
+    uint32_t tab = L.dirtab[d];
+    uint32_t mMid = tab & 0x1ff, mBack = (tab >> 9) & 0x1ff, mFront = tab >> 18;
+    noop = false;
+    if (BEH == AGG || BEH == LOCO) {
+        uint32_t S = win9<RW>(L.p0, sr, sc), T = win9<RW>(L.p0, tr, tc);
+        uint32_t gi = (__popc(S & mBack) * 3 + __popc(S & mMid)) * 4 + __popc(T & mFront);
+        if (BEH == LOCO) {
+            uint32_t cur = loco_sense(L.light, g.orient, (int)g.a, (int)sr - 1, (int)sc - 1);
+            uint32_t fut = loco_sense(L.light, g.orient, (int)g.a, (int)tr - 1, (int)tc - 1);
+            uint32_t li = (cur == fut) ? 2u : cur;           // (0,1)->0 (1,0)->1 else 2; locomotion.rs:230-235
+            gi += li * 48u;
+        }
+        return L.thr[gi];
+    } else if (BEH == COAT) {
+        uint32_t Sp = win9<RW>(L.p0, sr, sc), Tp = win9<RW>(L.p0, tr, tc);
+        uint32_t So = win9<RW>(L.p2, sr, sc), To = win9<RW>(L.p2, tr, tc);
+        uint32_t b = coat_idx3(__popc(Sp & mBack), __popc(So & mBack));
+        uint32_t m = coat_idx2(__popc(Sp & mMid), __popc(So & mMid));
+        uint32_t f = coat_idx3(__popc(Tp & mFront), __popc(To & mFront));
+        return L.thr[(b * 6 + m) * 10 + f];
+    } else {
+        uint32_t S0 = win9<RW>(L.p0, sr, sc), S1 = win9<RW>(L.p1, sr, sc);
+        uint32_t T0 = win9<RW>(L.p0, tr, tc), T1 = win9<RW>(L.p1, tr, tc);
+        uint32_t oS = S0 | S1, oT = T0 | T1;
+        uint32_t col = sep_colour(g, idx);
+        uint32_t sS = same_mask(S0, S1, col), sT = same_mask(T0, T1, col);
+        uint32_t b = sep_idx(__popc(oS & mBack), __popc(sS & mBack));
+        uint32_t m = sep_idx(__popc(oS & mMid), __popc(sS & mMid));
+        uint32_t f = sep_idx(__popc(oT & mFront), __popc(sT & mFront));
+        uint32_t th = L.thr[(b * 6 + m) * 10 + f];
+        if (kind == 2) {
+            // the partner (at t) evaluated for the flipped move t -> s (separation.rs:768-778):
+            // its BACK is our FRONT, its FRONT our BACK, "same colour" relative to ITS colour.
+            uint32_t col2 = ((T0 >> 4) & 1u) | (((T1 >> 4) & 1u) << 1);
+            uint32_t pS = same_mask(S0, S1, col2), pT = same_mask(T0, T1, col2);
+            uint32_t b2 = sep_idx(__popc(oT & mFront), __popc(pT & mFront));
+            uint32_t m2 = sep_idx(__popc(oS & mMid), __popc(pS & mMid));
+            uint32_t f2 = sep_idx(__popc(oS & mBack), __popc(pS & mBack));
+            uint32_t th2 = L.thr[(b2 * 6 + m2) * 10 + f2];
+            th = min(th, th2);                               // max gene == min probability (tables are non-increasing)
+            noop = (col2 == col);                            // drawn and accepted but nothing moves (separation.rs:287-288)
+        }
+        return th;
+    }
+}
+
+// --- commit of lane f's accepted proposal; called by ALL lanes with f's data broadcast -----------------
+template <int BEH, int RW>
+__device__ __forceinline__ void commit(const Lat& L, const Geo& g, uint32_t lane, uint32_t f,
+                                       uint32_t idxf, uint32_t sf, uint32_t tf, uint32_t kindf) {
+    uint32_t sr = sf & 0xff, sc = sf >> 8, tr = tf & 0xff, tc = tf >> 8;
+    if (BEH == SEP) {
+        uint32_t col = sep_colour(g, idxf);
+        uint32_t partner = 0xffffffffu;
+        uint32_t x = col;                                    // bits to flip at both cells
+        if (kindf == 2) {
+            // swap: find the partner's index (the reference's participants.iter().position scan,
+            // separation.rs:302) with a warp-wide scan; effective swaps are ~0.3 % of attempts
+            for (uint32_t base = 0; base < g.n; base += 32) {
+                uint32_t i = base + lane;
+                uint32_t hit = __ballot_sync(0xffffffffu, i < g.n && L.pos[i] == tf);
+                if (hit) { partner = base + __ffs(hit) - 1; break; }
+            }
+            x = col ^ sep_colour(g, partner);
+        }
+        if (lane == f) {
+            if (x & 1) { Plane<RW>::flip(L.p0, sr, sc); Plane<RW>::flip(L.p0, tr, tc); }
+            if (x & 2) { Plane<RW>::flip(L.p1, sr, sc); Plane<RW>::flip(L.p1, tr, tc); }
+            L.pos[idxf] = (uint16_t)tf;
+            if (kindf == 2) L.pos[partner] = (uint16_t)sf;
+        }
+    } else {
+        if (lane == f) {
+            if (BEH == LOCO) {                               // locomotion.rs:344-519, net effect (see oracle)
+                int a = (int)g.a, sx = (int)sr - 1, sy = (int)sc - 1, tx = (int)tr - 1, ty = (int)tc - 1;
+                uint32_t cur = loco_sense(L.light, g.orient, a, sx, sy);
+                uint32_t fut = loco_sense(L.light, g.orient, a, tx, ty);
+                if (cur) L.light[loco_beam(g.orient, a, sx, sy)] = (uint16_t)(sx | (sy << 8));
+                if (fut) L.light[loco_beam(g.orient, a, tx, ty)] = (uint16_t)(tx | (ty << 8));
+            }
+            Plane<RW>::flip(L.p0, sr, sc); Plane<RW>::flip(L.p0, tr, tc);
+            Plane<RW>::flip(L.p1, sr, sc); Plane<RW>::flip(L.p1, tr, tc);
+            L.pos[idxf] = (uint16_t)tf;
+        }
+    }
+    __syncwarp();
+}
+
+// --- resolve one speculative batch -----------------------------------------------------------------
+// `active` lanes hold consecutive chain steps in lane order; `eff` lanes want to change the state.
+// Commits in order, cutting the batch at the first lane whose evaluation a commit invalidated.
+// Returns the lane bound R: active lanes < R are retired.  ncommit counts committed moves.
+template <int BEH, int RW>
+__device__ __forceinline__ uint32_t resolve(const Lat& L, const Geo& g, uint32_t lane, bool active, bool eff,
+                                            uint32_t idx, uint32_t s, uint32_t t, uint32_t kind, uint32_t& ncommit) {
+    uint32_t A = __ballot_sync(0xffffffffu, eff);
+    uint32_t R = 32;
+    while (A) {
+        uint32_t f = __ffs(A) - 1;
+        uint32_t idxf = __shfl_sync(0xffffffffu, idx, f);
+        uint32_t sf = __shfl_sync(0xffffffffu, s, f);
+        uint32_t tf = __shfl_sync(0xffffffffu, t, f);
+        uint32_t kindf = (BEH == SEP) ? __shfl_sync(0xffffffffu, kind, f) : 1u;
+        commit<BEH, RW>(L, g, lane, f, idxf, sf, tf, kindf);
+        ++ncommit;
+        bool cf = false;
+        if (active && lane > f && lane < R) {
+            if (kind == 0) {
+                cf = (s == sf) | (s == tf) | (t == sf) | (t == tf);
+            } else {
+                cf = adj_or_eq(sf, s) | adj_or_eq(sf, t) | adj_or_eq(tf, s) | adj_or_eq(tf, t);
+                if (BEH == LOCO) {                           // the light table is part of the read set
+                    int a = (int)g.a;
+                    int b1 = loco_beam(g.orient, a, (int)(sf & 0xff) - 1, (int)(sf >> 8) - 1);
+                    int b2 = loco_beam(g.orient, a, (int)(tf & 0xff) - 1, (int)(tf >> 8) - 1);
+                    int bs = loco_beam(g.orient, a, (int)(s & 0xff) - 1, (int)(s >> 8) - 1);
+                    int bt = loco_beam(g.orient, a, (int)(t & 0xff) - 1, (int)(t >> 8) - 1);
+                    cf |= (bs == b1) | (bs == b2) | (bt == b1) | (bt == b2);
+                }
+            }
+        }
+        uint32_t C = __ballot_sync(0xffffffffu, cf);
+        if (C) R = __ffs(C) - 1;
+        A &= ~((2u << f) - 1u);
+        A &= lowmask(R);
+    }
+    return R;
+}
+
+// --- initial configuration ---------------------------------------------------------------------------
+template <int BEH, int RW>
+__device__ __forceinline__ uint32_t init_instance(const KParams& P, const Lat& L, const Geo& g, const Instance& in, uint32_t lane) {
+    const uint32_t G = g.G, a = g.a, PG = G + 2;
+    uint32_t* blocked = (BEH == SEP) ? L.p2 : L.p1;
+    for (uint32_t w = lane; w < P.plane_words; w += 32) {
+        L.p0[w] = 0; L.p1[w] = 0;
+        if (BEH == SEP || BEH == COAT) L.p2[w] = 0;
+    }
+    __syncwarp();
+    // static "not enterable" mask: everything except arena cells |i - j| <= a (mod.rs:115-122)
+    for (uint32_t r = lane; r < PG; r += 32) {
+#pragma unroll
+        for (int w = 0; w < RW; ++w) {
+            uint32_t m = 0xffffffffu;
+            if (r >= 1 && r <= G) {
+                int lo = (int)r - (int)a; if (lo < 1) lo = 1;
+                int hi = (int)r + (int)a; if (hi > (int)G) hi = (int)G;
+                lo -= 32 * w; hi -= 32 * w;
+                if (lo < 0) lo = 0;
+                if (hi > 31) hi = 31;
+                if (lo <= hi) {
+                    uint32_t v = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+                    m = ~v;
+                }
+            }
+            blocked[r * RW + w] = m;
+        }
+    }
+    __syncwarp();
+    if (BEH == COAT) {                                       // object hexagon, coating.rs:261-284
+        uint32_t o = in.layers, c = in.coat, side = 2 * o + 1, base = a - o + c + 1;   // +1: padded
+        for (uint32_t k = lane; k < side * side; k += 32) {
+            uint32_t u = k / side, v = k % side;
+            int dd = (int)u - (int)v;
+            if (dd <= (int)o && dd >= -(int)o) {
+                Plane<RW>::atom_or(L.p2, base + u, base + v);
+                Plane<RW>::atom_or(L.p1, base + u, base + v);
+            }
+        }
+        __syncwarp();
+    }
+    // seeded rejection placement (mod.rs:125-137): lane l expands ChaCha12 block (base + l) = 4 candidate
+    // cells; candidates are then consumed 32 at a time in stream order.
+    uint32_t key[8];
+    stdrng_key(in.seed, key);
+    const uint64_t zone = ~(uint64_t)0 - ((0 - (uint64_t)G) % G);
+    uint32_t placed = 0, status = 0;
+    for (uint64_t blk = 0; placed < g.n; blk += 32) {
+        uint32_t w[16];
+        chacha12_block(key, blk + lane, w);
+        uint32_t cand[4];
+        bool rej = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint64_t vi = (uint64_t)w[4 * k] | ((uint64_t)w[4 * k + 1] << 32);
+            uint64_t vj = (uint64_t)w[4 * k + 2] | ((uint64_t)w[4 * k + 3] << 32);
+            rej |= (vi * G > zone) | (vj * G > zone);
+            uint32_t i = (uint32_t)__umul64hi(vi, (uint64_t)G), j = (uint32_t)__umul64hi(vj, (uint64_t)G);
+            cand[k] = (i + 1) | ((j + 1) << 8);
+        }
+        if (__any_sync(0xffffffffu, rej)) status = 1;        // Uniform zone rejection (p ~ G/2^64): not replayed
+        uint32_t c01 = cand[0] | (cand[1] << 16), c23 = cand[2] | (cand[3] << 16);
+        for (uint32_t sub = 0; sub < 4 && placed < g.n; ++sub) {
+            uint32_t src = sub * 8 + (lane >> 2), slot = lane & 3;
+            uint32_t a01 = __shfl_sync(0xffffffffu, c01, src), a23 = __shfl_sync(0xffffffffu, c23, src);
+            uint32_t cell = (((slot & 2) ? a23 : a01) >> ((slot & 1) * 16)) & 0xffffu;
+            uint32_t pr = cell & 0xff, pc = cell >> 8;
+            bool free_ = true;
+            if (BEH == SEP) free_ = !(Plane<RW>::bit(L.p0, pr, pc) | Plane<RW>::bit(L.p1, pr, pc) | Plane<RW>::bit(L.p2, pr, pc));
+            else free_ = !Plane<RW>::bit(L.p1, pr, pc);
+            uint32_t same = __match_any_sync(0xffffffffu, cell);
+            bool acc = free_ && (lane == (uint32_t)(__ffs(same) - 1));
+            uint32_t am = __ballot_sync(0xffffffffu, acc);
+            uint32_t ord = placed + __popc(am & lowmask(lane));
+            if (acc && ord < g.n) {
+                L.pos[ord] = (uint16_t)cell;
+                if (BEH == SEP) {
+                    uint32_t col = sep_colour(g, ord);
+                    if (col & 1) Plane<RW>::atom_or(L.p0, pr, pc);
+                    if (col & 2) Plane<RW>::atom_or(L.p1, pr, pc);
+                } else {
+                    Plane<RW>::atom_or(L.p0, pr, pc);
+                    Plane<RW>::atom_or(L.p1, pr, pc);
+                }
+            }
+            placed += __popc(am);
+            __syncwarp();
+        }
+    }
+    if (BEH == LOCO) {
+        // light table: zig-zag initial fronts (locomotion.rs:116-168) raised to the front-most
+        // particle of each beam during placement (199-225).  The sequential "replace if >=" rule is
+        // order independent (a running maximum), so it is rebuilt here with shared-memory atomicMax.
+        uint32_t* tmp = reinterpret_cast<uint32_t*>(L.thr);  // thresholds are staged afterwards
+        const uint32_t o = g.orient, nb = 2 * a + 1;
+        for (uint32_t b = lane; b < nb; b += 32) {
+            uint32_t x, y;
+            if (o == 3) { x = (b + 1) / 2; y = a + b / 2; }
+            else { x = (b + 1) / 2; y = b & 1; }
+            L.light[b] = (uint16_t)(x | (y << 8));
+            tmp[b] = 0;
+        }
+        __syncwarp();
+        for (uint32_t k = lane; k < g.n; k += 32) {
+            uint32_t cell = L.pos[k];
+            int x = (int)(cell & 0xff) - 1, y = (int)(cell >> 8) - 1;
+            int b; uint32_t val, keyv;
+            if (o == 1) { b = 2 * x - y; val = (uint32_t)y; keyv = ((uint32_t)y << 8) | (uint32_t)x; }
+            else if (o == 2) { b = 2 * y - x; val = (uint32_t)x; keyv = ((uint32_t)x << 8) | (uint32_t)y; }
+            else { b = x + y - (int)a; val = (uint32_t)x; keyv = ((uint32_t)x << 8) | (uint32_t)y; }
+            bool ok = (o == 3) ? (x + y >= (int)a && x + y < 3 * (int)a) : (b >= 0 && b <= 2 * (int)a);
+            if (ok) {
+                uint32_t init = L.light[b];
+                uint32_t iv = (o == 1) ? (init >> 8) : (init & 0xff);
+                if (val >= iv) atomicMax(&tmp[b], keyv + 1);
+            }
+        }
+        __syncwarp();
+        for (uint32_t b = lane; b < nb; b += 32) {
+            uint32_t kv = tmp[b];
+            if (kv) {
+                kv -= 1;
+                uint32_t hi = kv >> 8, lo = kv & 0xff;
+                uint32_t x = (o == 1) ? lo : hi, y = (o == 1) ? hi : lo;
+                L.light[b] = (uint16_t)(x | (y << 8));
+            }
+        }
+        __syncwarp();
+    }
+    // genome -> acceptance thresholds (gene_probability(), mod.rs:85-87)
+    const uint8_t* gen = P.genomes + (size_t)in.genome * P.genome_len;
+    for (uint32_t k = lane; k < P.genome_len; k += 32) L.thr[k] = P.prob[gen[k] & 15];
+    __syncwarp();
+    return status;
+}
+
+// --- fitness integers ---------------------------------------------------------------------------------
+template <int BEH, int RW>
+__device__ __forceinline__ void fitness(const KParams& P, const Lat& L, const Geo& g, const Instance& in, uint32_t lane,
+                                        uint32_t& i0, uint32_t& i1) {
+    uint32_t s0 = 0, s1 = 0;
+    for (uint32_t k = lane; k < g.n; k += 32) {
+        uint32_t cell = L.pos[k], r = cell & 0xff, c = cell >> 8;
+        if (BEH == AGG || BEH == LOCO) {
+            s0 += __popc(win9<RW>(L.p0, r, c) & NB_MASK);                       // mod.rs:166-178
+            if (BEH == LOCO) {
+                int x = (int)r - 1, y = (int)c - 1;
+                s1 += g.orient == 1 ? (uint32_t)y : g.orient == 2 ? (uint32_t)x : (uint32_t)(x - y + (int)g.a);
+            }
+        } else if (BEH == SEP) {
+            uint32_t w0 = win9<RW>(L.p0, r, c), w1 = win9<RW>(L.p1, r, c);
+            s0 += __popc((w0 | w1) & NB_MASK);                                  // separation.rs:255-275
+            s1 += __popc(same_mask(w0, w1, sep_colour(g, k)) & NB_MASK);
+        } else {
+            uint32_t dv = P.coat_dist[in.aux + (r - 1) * g.G + (c - 1)];        // coating.rs:561-574
+            if (dv != 0xFFFFu) s1 += dv;
+        }
+    }
+    i0 = __reduce_add_sync(0xffffffffu, s0);
+    i1 = __reduce_add_sync(0xffffffffu, s1);
+}
+
+// --- one instance, start to finish ------------------------------------------------------------------
+template <int BEH, int RW, int MODE>
+__device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, const Instance& in, uint32_t lane) {
+    Geo g;
+    g.a = in.arena; g.G = 2 * g.a + 1; g.orient = in.orient;
+    {
+        uint32_t p = in.layers, t = p + in.coat;
+        g.n = BEH == AGG ? 3 * p * (p + 1) + 1 : BEH == COAT ? 3 * t * (t + 1) - 3 * p * (p + 1) : 3 * p * (p + 1);
+    }
+    g.n3 = g.n / 3;
+    uint32_t status = init_instance<BEH, RW>(P, L, g, in, lane);
+
+    const uint64_t steps = in.steps, ms = in.move_seed;
+    const uint32_t n = g.n;
+    uint64_t k = 0, nposs = 0;
+    uint32_t ncommit = 0;
+
+    if (MODE == MODE_FAST) {
+        const uint32_t key = (uint32_t)ms, khi = (uint32_t)(ms >> 32);
+        while (k < steps) {
+            uint64_t rem = steps - k;
+            uint64_t st = k + lane;
+            uint32_t r0, r1;
+            philox2x32_10((uint32_t)st, (uint32_t)(st >> 32) ^ khi, key, r0, r1);
+            uint32_t idx = __umulhi(r0, n);
+            uint64_t m6 = (uint64_t)r1 * 6u;
+            uint32_t d = (uint32_t)(m6 >> 32), plo = (uint32_t)m6;
+            uint32_t s, t, kind;
+            probe<BEH, RW>(L, idx, d, s, t, kind);
+            bool active = (uint64_t)lane < rem;
+            bool poss = active && kind != 0;
+            bool eff = false;
+            if (poss) {
+                bool noop;
+                uint32_t thr = threshold<BEH, RW>(L, g, idx, d, s, t, kind, noop);
+                eff = (__umulhi(plo, 1000u) < thr) && !noop;
+            }
+            uint32_t pm = __ballot_sync(0xffffffffu, poss);
+            uint32_t R = resolve<BEH, RW>(L, g, lane, active, eff, idx, s, t, poss ? kind : 0u, ncommit);
+            uint32_t lim = rem < (uint64_t)R ? (uint32_t)rem : R;
+            nposs += __popc(pm & lowmask(lim));
+            k += lim;
+        }
+    } else {
+        uint64_t cbase = 0;                                  // thread-local draws consumed so far
+        while (k < steps) {
+            uint64_t rem = steps - k;
+            // raw draws cbase + 2l + 1 (even slot) and cbase + 2l + 2 (odd slot)
+            const uint64_t kE = cbase + 2 * lane + 1, kO = kE + 1;
+            uint64_t rE = wy_draw(ms, kE), rO = wy_draw(ms, kO);
+            uint64_t nE = __shfl_down_sync(0xffffffffu, rE, 1);
+            uint32_t nO32 = __shfl_down_sync(0xffffffffu, (uint32_t)rO, 1);
+            // a step starting in the even slot uses (rE, rO, next rE); in the odd slot (rO, next rE, next rO)
+            uint32_t idxE = wy_mod_u64(rE, n, ms, kE), dE = wy_mod_u64(rO, 6, ms, kO);
+            uint32_t idxO = wy_mod_u64(rO, n, ms, kO), dO = wy_mod_u64(nE, 6, ms, kO + 1);
+            uint32_t sE, tE, kindE, sO, tO, kindO;
+            probe<BEH, RW>(L, idxE, dE, sE, tE, kindE);
+            probe<BEH, RW>(L, idxO, dO, sO, tO, kindO);
+            const uint32_t PE = __ballot_sync(0xffffffffu, kindE != 0), PO = __ballot_sync(0xffffffffu, kindO != 0);
+            // which slots start a real step: a blocked step consumes 2 draws, a possible one 3
+            uint32_t realE = 0, realO = 0, l = 0, par = 0;
+            while (l < 31) {
+                uint32_t m = ((par ? PO : PE) >> l) & ((1u << (31 - l)) - 1u);
+                uint32_t upto = m ? l + (uint32_t)__ffs(m) - 1 : 30u;
+                uint32_t mask = ((2u << upto) - 1u) & ~((1u << l) - 1u);
+                if (par) realO |= mask; else realE |= mask;
+                if (!m) { l = 31; break; }
+                if (par) { l = upto + 2; par = 0; } else { l = upto + 1; par = 1; }
+            }
+            const uint32_t q_end = 2 * l + par;
+            const bool myO = (realO >> lane) & 1u, myE = (realE >> lane) & 1u;
+            const uint32_t ord = __popc((realE | realO) & lowmask(lane));
+            const bool active = (myE || myO) && (uint64_t)ord < rem;
+            uint32_t idx = myO ? idxO : idxE, d = myO ? dO : dE, s = myO ? sO : sE, t = myO ? tO : tE;
+            uint32_t kind = myO ? kindO : kindE;
+            bool poss = active && kind != 0;
+            bool eff = false;
+            if (poss) {
+                bool noop;
+                uint32_t thr = threshold<BEH, RW>(L, g, idx, d, s, t, kind, noop);
+                uint32_t pd = wy_mod_1000(myO ? nO32 : (uint32_t)nE, ms, (myO ? kO : kE) + 2);
+                eff = (pd < thr) && !noop;
+            }
+            uint32_t pm = __ballot_sync(0xffffffffu, poss);
+            uint32_t am = __ballot_sync(0xffffffffu, active);
+            uint32_t R = resolve<BEH, RW>(L, g, lane, active, eff, idx, s, t, poss ? kind : 0u, ncommit);
+            nposs += __popc(pm & lowmask(R));
+            k += __popc(am & lowmask(R));
+            if (R < 32) cbase += 2 * R + __shfl_sync(0xffffffffu, (uint32_t)myO, R);   // the cut lane restarts the next batch
+            else cbase += q_end;
+        }
+    }
+
+    uint32_t i0, i1;
+    fitness<BEH, RW>(P, L, g, in, lane, i0, i1);
+    if (lane == 0) {
+        DevResult r; r.i0 = i0; r.i1 = i1; r.i2 = (BEH == LOCO) ? g.orient : 0u; r.status = status;
+        P.out[in.slot] = r;
+        atomicAdd(&P.counters[0], (unsigned long long)steps);
+        atomicAdd(&P.counters[1], (unsigned long long)nposs);
+        atomicAdd(&P.counters[2], (unsigned long long)ncommit);
+    }
+    if (P.dump) {
+        uint32_t* dst = P.dump + (size_t)(in.slot - P.dump_slot0) * P.dump_stride;
+        const uint32_t pw = P.plane_words;
+        for (uint32_t w = lane; w < pw; w += 32) {
+            dst[w] = L.p0[w]; dst[pw + w] = L.p1[w];
+            dst[2 * pw + w] = (BEH == SEP || BEH == COAT) ? L.p2[w] : 0u;
+        }
+        const uint32_t* pos32 = reinterpret_cast<const uint32_t*>(L.pos);
+        for (uint32_t w = lane; w < (g.n + 1) / 2; w += 32) dst[3 * pw + w] = pos32[w];
+        if (BEH == LOCO) {
+            const uint32_t* l32 = reinterpret_cast<const uint32_t*>(L.light);
+            dst[3 * pw + P.pos_words + lane] = l32[lane];
+        }
+    }
+    __syncwarp();
+}
+
+template <int BEH, int RW, int MODE>
+__global__ void __launch_bounds__(256) sops_chain_kernel(const KParams P) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ uint32_t s_dirtab[8];
+    if (threadIdx.x < 6) s_dirtab[threadIdx.x] = dir_word((int)threadIdx.x);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* base = smem + (size_t)warp * P.words_per_warp;
+    Lat L;
+    L.p0 = base + P.off_p0; L.p1 = base + P.off_p1; L.p2 = base + P.off_p2;
+    L.pos = reinterpret_cast<uint16_t*>(base + P.off_pos);
+    L.thr = reinterpret_cast<uint16_t*>(base + P.off_thr);
+    L.light = reinterpret_cast<uint16_t*>(base + P.off_aux);
+    L.dirtab = s_dirtab;
+    for (;;) {
+        uint32_t q = 0;
+        if (lane == 0) q = atomicAdd(P.work_counter, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= P.n_inst) break;
+        const Instance in = P.inst[q];
+        run_instance<BEH, RW, MODE>(P, L, in, lane);
+    }
+}
+
+}  // namespace sops

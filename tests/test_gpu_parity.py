@@ -1,0 +1,170 @@
+"""GPU parity: the CUDA chain kernels, called through the C ABI, against the CPU oracle on the same
+seeded inputs.  Integers, final lattices and particle lists must be bit-exact in BOTH rng modes (the
+oracle implements the same Philox stream for fast mode); float fitness within 1e-6 relative."""
+import numpy as np
+import pytest
+
+import evosops_b200 as E
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+W = {E.AGG: (0.0, 0.0), E.SEP: (0.65, 0.35), E.COAT: (0.65, 0.35), E.LOCO: (0.75, 0.25)}
+
+
+def run_pair(ctx, beh, gs, sizes, seeds, rng_mode, steps=0, move_seeds=None, orient=None, flags=0):
+    w1, w2 = W[beh]
+    got = ctx.eval_batch(beh, gs, sizes, seeds, w1=w1, w2=w2, rng_mode=rng_mode, move_seeds=move_seeds,
+                         orient=orient, steps_override=steps, flags=flags | E.F_DUMP)
+    want, cnt = O.eval_batch(beh, gs, sizes, seeds, w1=w1, w2=w2, rng_mode=rng_mode, move_seeds=move_seeds,
+                             orient=orient, steps_override=steps, prob_table=1 if flags & E.F_THEORY_TABLE else 0)
+    return got, want, cnt
+
+
+def check_equal(ctx, beh, gs, sizes, seeds, got, want, cnt, rng_mode, steps, move_seeds=None, orient=None, flags=0,
+                dump_every=1):
+    for k in ("i0", "i1", "i2"):
+        assert np.array_equal(got[k], want[k]), (k, got[k], want[k])
+    assert np.allclose(got["f"], want["f"], rtol=1e-6, atol=0)
+    assert np.allclose(got["norm"], want["norm"], rtol=1e-6, atol=0)
+    c = ctx.counters()
+    assert (c["attempts"], c["possible"], c["committed"]) == tuple(int(v) for v in cnt)
+    # final lattice + particle list, instance by instance
+    w1, w2 = W[beh]
+    gs2 = np.asarray(gs, dtype=np.uint8).reshape(-1, E.GENOME_LEN[beh])
+    T = len(seeds)
+    for q in range(0, gs2.shape[0] * T, dump_every):
+        g, t = divmod(q, T)
+        ms = seeds[t] if move_seeds is None else int(np.asarray(move_seeds).reshape(-1)[q])
+        ori = 1 if orient is None else int(np.asarray(orient).reshape(-1)[q])
+        env = O.Env(beh, gs2[g], *sizes[t], seed=seeds[t], w1=w1, w2=w2, rng_mode=rng_mode, move_seed=ms,
+                    orientation=ori, prob_table=1 if flags & E.F_THEORY_TABLE else 0)
+        env.step(steps if steps else env.sim_duration)
+        grid, parts = ctx.dump_state(q, env.G, env.n)
+        assert np.array_equal(grid, env.grid()), "lattice differs at instance %d" % q
+        assert np.array_equal(parts, env.particles()), "particle list differs at instance %d" % q
+
+
+@pytest.mark.parametrize("rng_mode", [E.RNG_VERIFY, E.RNG_FAST])
+@pytest.mark.parametrize("beh", [E.AGG, E.SEP, E.COAT, E.LOCO])
+def test_init_only_matches_oracle(ctx, genomes, beh, rng_mode):
+    name = {E.AGG: "agg_random", E.SEP: "sep_random", E.COAT: "coat_random", E.LOCO: "loco_random"}[beh]
+    sizes = [(20, 5, 2), (26, 8, 4), (12, 2, 1)] if beh == E.COAT else [(6, 3), (10, 7), (13, 9), (20, 14), (26, 18)]
+    seeds = [1, 62813, 71729]
+    tsz = [s for s in sizes for _ in seeds]
+    tsd = [sd for _ in sizes for sd in seeds]
+    orient = (np.arange(len(tsz)) % 3 + 1).astype(np.uint8) if beh == E.LOCO else None
+    w1, w2 = W[beh]
+    got = ctx.eval_batch(beh, genomes[name], tsz, tsd, w1=w1, w2=w2, rng_mode=rng_mode, orient=orient,
+                         flags=E.F_DUMP | E.F_INIT_ONLY)
+    for t in range(len(tsz)):
+        env = O.Env(beh, genomes[name], *tsz[t], seed=tsd[t], w1=w1, w2=w2,
+                    orientation=1 if orient is None else int(orient[t]))
+        r = env.fitness()
+        assert (got[0, t]["i0"], got[0, t]["i1"], got[0, t]["i2"]) == (r.i0, r.i1, r.i2)
+        assert abs(got[0, t]["f"] - r.f) <= 1e-6 * abs(r.f)
+        grid, parts = ctx.dump_state(t, env.G, env.n)
+        assert np.array_equal(grid, env.grid()) and np.array_equal(parts, env.particles())
+
+
+def test_init_reproduces_reference_snapshots(ctx, fixtures, genomes):
+    # the reference's own step-0 lattices (misc_scripts/generate_tikz_img_{agg,sep}.py)
+    ctx.eval_batch(E.AGG, genomes["agg_theory"], [(13, 9)], [62813], flags=E.F_DUMP | E.F_INIT_ONLY | E.F_THEORY_TABLE)
+    grid, parts = ctx.dump_state(0, 27, 271)
+    assert np.array_equal(grid, np.asarray(fixtures["agg_13_9_snapshots"][0], dtype=np.uint8))
+    assert tuple(parts[0][:2]) == (12, 23) and tuple(parts[-1][:2]) == (9, 19)
+    got = ctx.eval_batch(E.SEP, genomes["sep_evolved"], [(13, 9)], [71729], w1=0.65, w2=0.35, flags=E.F_DUMP | E.F_INIT_ONLY)
+    grid, parts = ctx.dump_state(0, 27, 270)
+    assert np.array_equal(grid, np.asarray(fixtures["sep_13_9_snapshots"][0], dtype=np.uint8))
+    assert (got[0, 0]["i0"], got[0, 0]["i1"]) == (762, 278) and abs(got[0, 0]["f"] - 0.39848387) < 4e-7
+
+
+@pytest.mark.parametrize("rng_mode", [E.RNG_VERIFY, E.RNG_FAST])
+def test_agg_full_chains_bit_exact(ctx, genomes, rng_mode):
+    gs = np.stack([genomes["agg_theory"].clip(0, 5), genomes["agg_evolved"], genomes["agg_random"]])
+    sizes = [(6, 3)] * 4 + [(10, 7)] * 2 + [(13, 9)]
+    seeds = [1, 2, 3, 4, 1, 2, 1]
+    got, want, cnt = run_pair(ctx, E.AGG, gs, sizes, seeds, rng_mode)
+    check_equal(ctx, E.AGG, gs, sizes, seeds, got, want, cnt, rng_mode, 0)
+
+
+@pytest.mark.parametrize("rng_mode", [E.RNG_VERIFY, E.RNG_FAST])
+def test_agg_theory_table(ctx, genomes, rng_mode):
+    gs = genomes["agg_theory"]
+    sizes, seeds = [(6, 3), (10, 7), (13, 9)], [1, 1, 62813]
+    got, want, cnt = run_pair(ctx, E.AGG, gs, sizes, seeds, rng_mode, flags=E.F_THEORY_TABLE)
+    check_equal(ctx, E.AGG, gs, sizes, seeds, got, want, cnt, rng_mode, 0, flags=E.F_THEORY_TABLE)
+
+
+@pytest.mark.parametrize("rng_mode", [E.RNG_VERIFY, E.RNG_FAST])
+def test_agg_many_seeds_short_chains(ctx, genomes, rng_mode):
+    # 32 move seeds per size incl. the two-word-row class (20,14) and (26,18); chains capped at 3e5 steps
+    gs = np.stack([genomes["agg_evolved"], genomes["agg_random"]])
+    sizes = [(6, 3)] * 8 + [(13, 9)] * 8 + [(20, 14)] * 8 + [(26, 18)] * 8
+    seeds = list(range(1, 33))
+    ms = (np.arange(2 * 32, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(12345))
+    got, want, cnt = run_pair(ctx, E.AGG, gs, sizes, seeds, rng_mode, steps=300000, move_seeds=ms)
+    check_equal(ctx, E.AGG, gs, sizes, seeds, got, want, cnt, rng_mode, 300000, move_seeds=ms, dump_every=3)
+
+
+@pytest.mark.parametrize("rng_mode", [E.RNG_VERIFY, E.RNG_FAST])
+def test_sep_chains_bit_exact(ctx, genomes, rng_mode):
+    gs = np.stack([genomes["sep_evolved"], genomes["sep_random"]])
+    sizes = [(6, 3), (6, 3), (10, 7), (13, 9), (20, 14)]
+    seeds = [1, 2, 3, 71729, 5]
+    got, want, cnt = run_pair(ctx, E.SEP, gs, sizes, seeds, rng_mode, steps=400000)
+    check_equal(ctx, E.SEP, gs, sizes, seeds, got, want, cnt, rng_mode, 400000)
+
+
+@pytest.mark.parametrize("rng_mode", [E.RNG_VERIFY, E.RNG_FAST])
+def test_sep_theory_table_full_small_chain(ctx, genomes, rng_mode):
+    gs = genomes["sep_theory"]
+    sizes, seeds = [(6, 3), (6, 3)], [1, 2]
+    got, want, cnt = run_pair(ctx, E.SEP, gs, sizes, seeds, rng_mode, flags=E.F_THEORY_TABLE)
+    check_equal(ctx, E.SEP, gs, sizes, seeds, got, want, cnt, rng_mode, 0, flags=E.F_THEORY_TABLE)
+
+
+@pytest.mark.parametrize("rng_mode", [E.RNG_VERIFY, E.RNG_FAST])
+def test_coat_chains_bit_exact(ctx, genomes, rng_mode):
+    rng = np.random.default_rng(7)
+    gs = np.stack([genomes["coat_random"], rng.integers(0, 4, size=600, dtype=np.uint8)])
+    sizes = [(20, 5, 2), (20, 5, 2), (26, 8, 4), (12, 2, 1)]
+    seeds = [1, 2, 3, 4]
+    got, want, cnt = run_pair(ctx, E.COAT, gs, sizes, seeds, rng_mode, steps=400000)
+    check_equal(ctx, E.COAT, gs, sizes, seeds, got, want, cnt, rng_mode, 400000)
+
+
+@pytest.mark.parametrize("rng_mode", [E.RNG_VERIFY, E.RNG_FAST])
+def test_loco_chains_bit_exact(ctx, genomes, rng_mode):
+    rng = np.random.default_rng(11)
+    gs = np.stack([genomes["loco_random"], rng.integers(0, 3, size=144, dtype=np.uint8)])
+    sizes = [(6, 3), (10, 7), (13, 9), (13, 9), (20, 14), (26, 18)]
+    seeds = [1, 2, 3, 4, 5, 6]
+    orient = np.asarray([[1, 2, 3, 1, 2, 3], [3, 1, 2, 2, 3, 1]], dtype=np.uint8)
+    got, want, cnt = run_pair(ctx, E.LOCO, gs, sizes, seeds, rng_mode, steps=400000, orient=orient)
+    check_equal(ctx, E.LOCO, gs, sizes, seeds, got, want, cnt, rng_mode, 400000, orient=orient)
+
+
+def test_errors_not_panics(ctx, genomes):
+    bad = genomes["agg_evolved"].copy()
+    bad[5] = 11
+    with pytest.raises(E.SopsError) as ei:
+        ctx.eval_batch(E.AGG, bad, [(6, 3)], [1])
+    assert ei.value.code == -2
+    with pytest.raises(E.SopsError) as ei:
+        ctx.eval_batch(E.AGG, genomes["agg_evolved"], [(3, 6)], [1])
+    assert ei.value.code == -3
+    with pytest.raises(E.SopsError) as ei:
+        ctx.eval_batch(E.AGG, genomes["agg_evolved"], [(40, 9)], [1])
+    assert ei.value.code == -4
+
+
+def test_results_independent_of_batch_composition(ctx, genomes):
+    # streams are keyed by (seed, move_seed), never by warp/CTA/slot: one instance alone == inside a batch
+    gs = np.stack([genomes["agg_evolved"], genomes["agg_random"]])
+    sizes, seeds = [(6, 3), (10, 7), (6, 3)], [9, 8, 7]
+    full = ctx.eval_batch(E.AGG, gs, sizes, seeds, rng_mode=E.RNG_FAST)
+    for g in range(2):
+        for t in range(3):
+            one = ctx.eval_batch(E.AGG, gs[g], [sizes[t]], [seeds[t]], rng_mode=E.RNG_FAST)
+            assert one[0, 0]["i0"] == full[g, t]["i0"]

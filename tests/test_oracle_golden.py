@@ -1,0 +1,222 @@
+"""Pin the CPU oracle against every artefact the reference holds for the hot path.
+
+The reference (DaymudeLab/EvoSOPS) ships no tests; its only fixtures are the lattice snapshots and genomes
+embedded in misc_scripts/ (lifted verbatim into tests/golden/reference_fixtures.json by make_golden.py).
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+
+def sha16(grid):
+    return hashlib.sha256(np.ascontiguousarray(grid, dtype=np.uint8).tobytes()).hexdigest()[:16]
+
+
+# ---------------------------------------------------------------- RNG stacks ---------------------
+def test_chacha20_rfc8439_zero_key_block():
+    # RFC 8439 §2.3.2-style check of the block function with 10 double rounds: all-zero key/counter/nonce
+    out = O.chacha_block(np.zeros(8, dtype=np.uint32), 0, 0, 10)
+    assert ["%08x" % w for w in out[:4]] == ["ade0b876", "903df1a0", "e56a5d40", "28bd8653"]
+
+
+def test_seed_from_u64_key_and_stream_62813():
+    key = O.stdrng_key(62813)
+    assert ["%08x" % w for w in key] == ["1bd6d5bd", "798704f5", "03cdbf0c", "a7f90767",
+                                          "829c2e5f", "a3ca95e9", "bd6e714e", "2a23dec8"]
+    u = O.stdrng_u64(62813, 6)
+    assert ["%016x" % int(v) for v in u] == ["7639101c2aa1aaba", "de147007003e83a6", "450a65f83bef6c76",
+                                             "29971f015524acd0", "3c6e7dcdb26432f4", "df5061b5f42929d1"]
+
+
+def test_philox2x32_known_answers():
+    # Random123 kat_vectors: philox2x32 10 rounds
+    assert [int(v) for v in O.philox2x32_10(0, 0, 0)] == [0xff1dae59, 0x6cd10df2]
+    assert [int(v) for v in O.philox2x32_10(0xffffffff, 0xffffffff, 0xffffffff)] == [0x2c3f628b, 0xab4fd7ad]
+    assert [int(v) for v in O.philox2x32_10(0x243f6a88, 0x85a308d3, 0x13198a2e)] == [0xdd7ce038, 0xf62a4c12]
+
+
+def test_wyrand_is_counter_based():
+    # state after k draws = seed + k*INC, so draw k is a pure function of (seed, k)
+    INC, XOR, M = 0xA0761D6478BD642F, 0xE7037ED1A0B428DB, (1 << 64) - 1
+    seed = 0x123456789ABCDEF
+    got = O.wyrand_u64(seed, 8)
+    for k in range(8):
+        s = (seed + (k + 1) * INC) & M
+        t = s * (s ^ XOR)
+        assert int(got[k]) == ((t & M) ^ (t >> 64))
+
+
+def test_move_draw_ranges():
+    d = O.move_draws(7, 4096, 271)
+    assert d[:, 0].max() < 271 and d[:, 1].max() < 6
+    assert d[:, 2].min() >= 1 and d[:, 2].max() <= 1000
+    # all six directions and a broad set of particles are hit
+    assert len(set(d[:, 1].tolist())) == 6 and len(set(d[:, 0].tolist())) > 250
+
+
+# ---------------------------------------------------------------- init (pinned) ------------------
+def test_agg_init_matches_reference_snapshot(fixtures, genomes):
+    env = O.Env(O.AGG, genomes["agg_theory"], 13, 9, seed=62813, prob_table=1)
+    ref = np.asarray(fixtures["agg_13_9_snapshots"][0], dtype=np.uint8)
+    assert env.n == 271 and env.G == 27
+    assert np.array_equal(env.grid(), ref)                       # 729/729 cells
+    p = env.particles()
+    assert [tuple(r[:2]) for r in p[:8]] == [(12, 23), (7, 4), (23, 22), (1, 11), (17, 18), (26, 14), (19, 23), (10, 2)]
+    assert tuple(p[-1][:2]) == (9, 19)
+    assert sha16(env.grid()) == "29b36745b3cc08c6"
+
+
+def test_sep_init_matches_reference_snapshot(fixtures, genomes):
+    env = O.Env(O.SEP, genomes["sep_evolved"], 13, 9, seed=71729)
+    ref = np.asarray(fixtures["sep_13_9_snapshots"][0], dtype=np.uint8)
+    assert env.n == 270
+    assert np.array_equal(env.grid(), ref)
+    p = env.particles()
+    assert [tuple(r) for r in p[:6]] == [(9, 2, 1), (16, 17, 1), (21, 23, 1), (19, 16, 1), (23, 22, 1), (15, 13, 1)]
+    assert tuple(p[89]) == (11, 5, 1) and tuple(p[90]) == (9, 9, 2) and tuple(p[91]) == (14, 9, 2)
+    assert tuple(p[-1]) == (13, 7, 3)
+    assert sha16(env.grid()) == "4d9159ce94c67e4d"
+
+
+@pytest.mark.parametrize("beh,size,seed,digest,first,last", [
+    (O.AGG, (6, 3), 1, "f5ef433c20650a1b", [(12, 8), (5, 2), (5, 9), (6, 5), (2, 0), (2, 1), (11, 5), (7, 3)], (4, 9)),
+    (O.AGG, (13, 9), 1, "68a7401769bad9ef", [(26, 18), (11, 4), (10, 19), (14, 10), (5, 1), (5, 3), (16, 7), (25, 15)], (15, 24)),
+    (O.AGG, (26, 18), 1, "80c438ecefa7b7a4", [(51, 36), (22, 9), (20, 37), (27, 20)], (39, 44)),
+    (O.SEP, (13, 9), 62813, "2101ee3d0d80afaa", [], None),
+    (O.SEP, (6, 3), 1, "fe550f96d13681e5", [], None),
+])
+def test_derived_init_vectors(beh, size, seed, digest, first, last):
+    g = np.zeros(O.GENOME_LEN[beh], dtype=np.uint8)
+    env = O.Env(beh, g, size[0], size[1], seed=seed)
+    assert sha16(env.grid()) == digest
+    p = env.particles()
+    assert [tuple(r[:2]) for r in p[:len(first)]] == first
+    if last:
+        assert tuple(p[-1][:2]) == last
+
+
+def test_census(fixtures):
+    a = np.asarray(fixtures["agg_13_9_snapshots"][0])
+    assert [(a == v).sum() for v in (0, 1, 2)] == [276, 271, 182]
+    s = np.asarray(fixtures["sep_13_9_snapshots"][0])
+    assert [(s == v).sum() for v in (0, 1, 2, 3, 4)] == [277, 90, 90, 90, 182]
+    c = np.asarray(fixtures["coat_20_5_2_snapshots"][0])
+    assert (c == 2).sum() == 91 and ((c == 1) | (c == 9)).sum() == 78 and (c == 7).sum() == 420
+
+
+# ---------------------------------------------------------------- evaluate_fitness (pinned) -------
+def test_agg_fitness_on_reference_snapshots(fixtures, genomes):
+    env = O.Env(O.AGG, genomes["agg_theory"], 13, 9, seed=62813, prob_table=1)
+    want = [395, 399, 515, 717]
+    for grid, edges in zip(fixtures["agg_13_9_snapshots"], want):
+        assert env.load_grid(grid) == 271
+        r = env.fitness()
+        assert (r.i0, r.i1) == (edges, 756)
+        assert r.norm == edges / 756
+
+
+def test_sep_fitness_on_reference_snapshots(fixtures, genomes):
+    env = O.Env(O.SEP, genomes["sep_evolved"], 13, 9, seed=71729, w1=0.65, w2=0.35)
+    want = [((762, 278), 0.39848387), ((822, 302), 0.43038887), ((1230, 606), 0.68259323), ((1488, 1334), 0.97620815)]
+    for grid, ((E, S), fit) in zip(fixtures["sep_13_9_snapshots"], want):
+        assert env.load_grid(grid) == 270
+        r = env.fitness()
+        assert (r.i0, r.i1) == (E, S)
+        assert abs(r.f - fit) <= 1e-6 * fit
+
+
+def test_coat_fitness_on_reference_snapshots(fixtures, genomes):
+    # the snapshots were made by an older init (object at rows 13..23 / cols 8..18) and mark "connected"
+    # particles with 9: load them as-is with 9 -> 1; the distance grid is recomputed from the loaded lattice
+    env = O.Env(O.COAT, genomes["coat_random"], 20, 5, 2, seed=1)
+    assert env.n == 78
+    want_par = [909, 914, 888, 473, 145, 122, 123, 121]
+    want_fit = [0.132013, 0.131291, 0.135135, 0.253700, 0.827586, 0.983607, 0.975610, 0.991736]
+    for grid, par, fit in zip(fixtures["coat_20_5_2_snapshots"], want_par, want_fit):
+        g = np.asarray(grid, dtype=np.uint8).copy()
+        g[g == 9] = 1
+        assert env.load_grid(g) == 78
+        d = env.dist_grid()
+        assert (d != 0xFFFF).sum() == 1170
+        r = env.fitness()
+        assert (r.i0, r.i1) == (120, par)
+        assert abs(r.f - fit) < 5e-6
+
+
+def test_coat_current_init_object_position(genomes):
+    env = O.Env(O.COAT, genomes["coat_random"], 20, 5, 2, seed=1)
+    g = env.grid()
+    rows, cols = np.where(g == 2)
+    assert (g == 2).sum() == 91 and rows.min() == 17 and rows.max() == 27 and cols.min() == 17 and cols.max() == 27
+    assert (g == 1).sum() == 78 and (g == 7).sum() == 420
+
+
+# ---------------------------------------------------------------- chain behaviour ----------------
+def test_invalid_inputs_are_errors(genomes):
+    with pytest.raises(ValueError):                              # BASELINE's "(3,6)": 127 particles, 37 cells
+        O.Env(O.AGG, genomes["agg_evolved"], 3, 6, seed=1)
+    bad = genomes["agg_evolved"].copy()
+    bad[0] = 11                                                   # gene past the 11-entry table (reference panics)
+    with pytest.raises(ValueError):
+        O.Env(O.AGG, bad, 6, 3, seed=1)
+
+
+def test_theory_aggregation_reaches_published_quality(genomes):
+    # authors' dashed line for the theory algorithm: 0.92 (misc_scripts/plotter_single_agg.py:92)
+    vals = []
+    for ms in range(1, 9):
+        env = O.Env(O.AGG, genomes["agg_theory"], 13, 9, seed=62813, move_seed=ms, prob_table=1)
+        vals.append(env.simulate().norm)
+    assert 0.88 < np.mean(vals) < 0.95
+
+
+def test_agg_chain_conserves_particles_and_counts(genomes):
+    env = O.Env(O.AGG, genomes["agg_evolved"], 10, 7, seed=3)
+    env.step(200000)
+    g, p = env.grid(), env.particles()
+    assert (g == 1).sum() == env.n == 169
+    assert all(g[x, y] == 1 for x, y, _ in p) and len({(x, y) for x, y, _ in p}) == env.n
+    steps, poss, acc = env.counters()
+    assert steps == 200000 and acc <= poss <= steps
+
+
+def test_sep_chain_conserves_colours(genomes):
+    env = O.Env(O.SEP, genomes["sep_evolved"], 10, 7, seed=3)
+    env.step(100000)
+    g, p = env.grid(), env.particles()
+    assert [(g == c).sum() for c in (1, 2, 3)] == [56, 56, 56]
+    assert all(g[x, y] == s for x, y, s in p)
+
+
+@pytest.mark.parametrize("orient", [1, 2, 3])
+def test_loco_chain_runs_and_keeps_light_in_range(genomes, orient):
+    env = O.Env(O.LOCO, genomes["loco_random"], 10, 7, seed=5, orientation=orient, w1=0.75, w2=0.25)
+    env.step(100000)
+    g = env.grid()
+    assert (g == 1).sum() == env.n == 168
+    li = env.light()
+    assert li.max() <= 20
+    r = env.fitness()
+    assert r.i2 == orient and 0.0 < r.f < 1.5
+
+
+def test_fast_mode_matches_verify_mode_in_distribution(genomes):
+    from scipy.stats import ks_2samp
+    size, steps = (6, 3), 37 ** 3
+    a = [O.Env(O.AGG, genomes["agg_evolved"], *size, seed=1, move_seed=1000 + k, rng_mode=0).simulate(steps).i0 for k in range(300)]
+    b = [O.Env(O.AGG, genomes["agg_evolved"], *size, seed=1, move_seed=5000 + k, rng_mode=1).simulate(steps).i0 for k in range(300)]
+    assert ks_2samp(a, b).pvalue > 1e-3
+
+
+def test_eval_batch_matches_single_envs(genomes):
+    gs = np.stack([genomes["agg_evolved"], genomes["agg_random"]])
+    sizes, seeds = [(6, 3), (6, 3), (8, 5)], [1, 2, 1]
+    out, cnt = O.eval_batch(O.AGG, gs, sizes, seeds, n_threads=2)
+    for gi in range(2):
+        for t in range(3):
+            r = O.Env(O.AGG, gs[gi], *sizes[t], seed=seeds[t]).simulate()
+            assert out[gi, t]["i0"] == r.i0 and out[gi, t]["norm"] == r.norm
+    assert cnt[0] == 2 * (37 ** 3 * 2 + 91 ** 3)
