@@ -1,0 +1,318 @@
+#!/usr/bin/env python3
+"""bench.py — particle-move attempts/s (and GA generations/s) of the SOPS fitness-evaluation hot path.
+
+A "step" is one GA generation's evaluation batch (what base_ga.rs:393-411's nested par_iter does):
+config C2 of BASELINE.json / SURVEY.md §8d — aggregation, pop 50 x sizes {(6,4),(10,7),(13,9)} x seeds 1..5
+= 750 independent chains of n^3 attempts each (6.24e9 attempts).  With --gpus N every rank evaluates its own
+50-genome shard of a 50*N population (weak scaling, no data-path collective; one max/sum reduce for the report).
+
+  value   attempts/s, inputs resident in HBM, CUDA-event time of the chain kernel on its own stream
+  e2e     the same through sops_eval_batch with HOST buffers (validation + H2D + kernel + D2H + float fitness)
+  --impl reference   the CPU oracle (the Rust reference cannot be built here: no cargo) on all host threads,
+                     each step a bounded sample (--ref-pop genomes of the 50)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SIZES_C2 = [(6, 4), (10, 7), (13, 9)]
+SEEDS_C2 = [1, 2, 3, 4, 5]
+POP_C2 = 50
+GENOME_SEED = 0x45766F534F5053          # "EvoSOPS" 
+
+
+def splitmix64(state):
+    state = (state + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    z = state
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return state, z ^ (z >> 31)
+
+
+def synthetic_genomes(first, count, length, gran=10):
+    """i.i.d. uniform genes in 0..=gran from SplitMix64; genome g depends only on its global index."""
+    out = np.zeros((count, length), dtype=np.uint8)
+    for g in range(count):
+        st = (GENOME_SEED + 0x632BE59BD9B4E019 * (first + g)) & 0xFFFFFFFFFFFFFFFF
+        for k in range(length):
+            st, z = splitmix64(st)
+            out[g, k] = z % (gran + 1)
+    return out
+
+
+def trial_list(sizes, seeds):
+    # base_ga.rs:356-362: sizes-major, seeds-minor
+    return [s for s in sizes for _ in seeds], [sd for _ in sizes for sd in seeds]
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 and len(r) >= 7] or [r for (_, r) in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "power_w_max": max(float(r[2]) for r in rows),
+                "samples": len(rows), "reasons": reasons}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except (OSError, ValueError):
+        return {"sm_max_mhz": 1965.0}, "fallback"
+
+
+def cpu_leg(pop, gran, n_threads, rng_mode):
+    """One bounded sample of the C2 batch on the host cores with the CPU oracle (checker code, timed as baseline)."""
+    from oracle import oracle as O
+    gs = synthetic_genomes(0, pop, 48, gran)
+    tsz, tsd = trial_list(SIZES_C2, SEEDS_C2)
+    t0 = time.perf_counter()
+    _, cnt = O.eval_batch(O.AGG, gs, tsz, tsd, rng_mode=rng_mode, n_threads=n_threads)
+    dt = time.perf_counter() - t0
+    return float(cnt[0]), dt
+
+
+def run_reference(args, rank, world):
+    from oracle import oracle as O
+    if rank != 0:
+        return
+    cores = O.lib().oracle_hardware_threads()
+    rng_mode = 0                       # the reference's own move stream (fastrand WyRand)
+    for _ in range(args.warmup):
+        cpu_leg(args.ref_pop, args.gran, cores, rng_mode)
+    attempts, secs = 0.0, 0.0
+    for _ in range(args.steps):
+        a, dt = cpu_leg(args.ref_pop, args.gran, cores, rng_mode)
+        attempts += a
+        secs += dt
+    v = attempts / secs
+    sample = "pop %d of %d genomes x %d sizes x %d seeds per step (oracle port, WyRand stream)" % (
+        args.ref_pop, POP_C2, len(SIZES_C2), len(SEEDS_C2))
+    line = {"impl": "reference", "metric": "particle-move attempts/s", "value": v, "unit": "attempts/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/u8 integer", "data": "synthetic",
+            "config": workload_config(args),
+            "generations_per_s": v / attempts_per_generation(), "population": POP_C2,
+            "cpu_baseline": {"value": v, "unit": "attempts/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "attempts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def attempts_per_generation():
+    tot = 0
+    for (a, p) in SIZES_C2:
+        n = 3 * p * (p + 1) + 1
+        tot += n ** 3 * len(SEEDS_C2) * POP_C2
+    return float(tot)
+
+
+def workload_config(args):
+    return {"workload": "C2: aggregation GA generation (-b agg -e ga), pop %d x sizes %s x seeds 1..5, gran %d, n^3 attempts per chain"
+            % (POP_C2, "".join("(%d,%d)" % s for s in SIZES_C2), args.gran),
+            "instances_per_gpu": POP_C2 * len(SIZES_C2) * len(SEEDS_C2), "rng": args.rng,
+            "sharding": "population sharded, %d genomes per GPU" % POP_C2,
+            "l2": "flushed between timed steps (256 MiB write); working set is shared-memory resident"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rng", default="fast", choices=["fast", "verify"])
+    ap.add_argument("--gran", type=int, default=10)
+    ap.add_argument("--ref-pop", type=int, default=16)
+    ap.add_argument("--no-extra", action="store_true", help="skip the verify-mode and sweep side measurements")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import evosops_b200 as E
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce(val, op):
+        if world == 1:
+            return float(val)
+        t = torch.tensor([val], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    ctx = E.Context(device_ids=[local])
+    mode = E.RNG_FAST if args.rng == "fast" else E.RNG_VERIFY
+    gs = synthetic_genomes(rank * POP_C2, POP_C2, 48, args.gran)
+    tsz, tsd = trial_list(SIZES_C2, SEEDS_C2)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def l2_flush():
+        flush.add_(1)
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg: prepare once (H2D), time K launches with CUDA events on the launch stream
+    ctx.prepare(E.AGG, gs, tsz, tsd, gran=args.gran, rng_mode=mode)
+    for _ in range(max(args.warmup, 3)):
+        ctx.launch()
+        ctx.sync()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_wall0 = time.time()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        l2_flush()
+        ctx.launch()
+        dev_ms += ctx.sync()
+    barrier()
+    t_wall1 = time.time()
+    res = ctx.collect()
+    cnt = ctx.counters()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    attempts_step = float(cnt["attempts"])
+    p_poss = cnt["possible"] / cnt["attempts"]
+    p_acc = cnt["committed"] / cnt["attempts"]
+    launches_step = cnt["launches"]
+    worst_ms = reduce(dev_ms, dist.ReduceOp.MAX if world > 1 else None)
+    total_attempts = reduce(attempts_step, dist.ReduceOp.SUM if world > 1 else None) * args.steps
+    value = total_attempts / (worst_ms * 1e-3)
+
+    # ---- end-to-end leg: the public call with host buffers, H2D + D2H inside the timed region
+    for _ in range(1):
+        ctx.eval_batch(E.AGG, gs, tsz, tsd, gran=args.gran, rng_mode=mode)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = ctx.eval_batch(E.AGG, gs, tsz, tsd, gran=args.gran, rng_mode=mode)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    cnt2 = ctx.counters()
+    e2e_worst = reduce(e2e_s, dist.ReduceOp.MAX if world > 1 else None)
+    e2e_value = total_attempts / e2e_worst
+    mean_fitness = float(res["norm"].mean())
+
+    extra = {}
+    if not args.no_extra:
+        # the other RNG mode on the same batch, and a throughput-bound sweep (config 5 style, capped chains)
+        other = E.RNG_VERIFY if mode == E.RNG_FAST else E.RNG_FAST
+        ctx.prepare(E.AGG, gs, tsz, tsd, gran=args.gran, rng_mode=other)
+        ctx.launch(); ctx.sync()
+        ctx.launch(); ms_o = ctx.sync()
+        ctx.collect()
+        v_o = reduce(attempts_step, dist.ReduceOp.SUM if world > 1 else None) / (reduce(ms_o, dist.ReduceOp.MAX if world > 1 else None) * 1e-3)
+        extra["verify_mode" if other == E.RNG_VERIFY else "fast_mode"] = {"value": v_o, "unit": "attempts/s", "ms_per_step": ms_o}
+        n_sweep, cap = 50000, 200000
+        seeds = list(range(1 + rank * n_sweep, 1 + (rank + 1) * n_sweep))
+        for nm, md in (("fast", E.RNG_FAST), ("verify", E.RNG_VERIFY)):
+            ctx.prepare(E.AGG, gs[:1], [(13, 9)] * n_sweep, seeds, gran=args.gran, rng_mode=md, steps_override=cap)
+            ctx.launch(); ctx.sync()
+            ctx.launch(); ms_s = ctx.sync()
+            ctx.collect()
+            tot = reduce(float(n_sweep) * cap, dist.ReduceOp.SUM if world > 1 else None)
+            extra["sweep_13_9_%s" % nm] = {"value": tot / (reduce(ms_s, dist.ReduceOp.MAX if world > 1 else None) * 1e-3),
+                                           "unit": "attempts/s", "instances_per_gpu": n_sweep, "steps_cap": cap}
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+        peak_smem = 148 * 128 * sm_mhz * 1e6 / 1e9                       # GB/s: 128 B/clk/SM
+        alg_bytes = 10.0 + 22.3 * p_poss + 18.0 * p_acc
+        k_ms = dev_ms / (args.steps * max(launches_step, 1))
+        achieved = alg_bytes * attempts_step / max(launches_step, 1) / (k_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except (OSError, ValueError):
+            pass
+        line = {"metric": "particle-move attempts/s", "value": value, "unit": "attempts/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": worst_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32/u64 integer",
+                "data": "synthetic", "config": workload_config(args),
+                "generations_per_s": 1e3 / (worst_ms / args.steps), "population": POP_C2 * world,
+                "e2e": {"value": e2e_value, "unit": "attempts/s", "h2d_bytes_per_step": cnt2["h2d_bytes"],
+                        "d2h_bytes_per_step": cnt2["d2h_bytes"], "ms_per_step": e2e_worst / args.steps * 1e3},
+                "gpu_launches": int(launches_step * args.steps),
+                "clocks": clocks,
+                "roofline": {"bound": "smem", "achieved": achieved, "peak": peak_smem, "unit": "GB/s",
+                             "frac": achieved / peak_smem, "traffic": traffic,
+                             "kernel": "sops_chain_kernel<AGG,RW=1,%s>" % args.rng, "kernel_ms": k_ms,
+                             "alg_bytes_per_attempt": alg_bytes, "p_poss": p_poss, "p_acc": p_acc,
+                             "peak_source": "%s sm_max_mhz x 148 SMs x 128 B/clk shared memory" % peak_src,
+                             "note": "chains are dependent-latency bound at 750 warps/GPU; see DESIGN.md"},
+                "mean_fitness": mean_fitness}
+        line.update(extra)
+        if world == 1:
+            import multiprocessing
+            cores = multiprocessing.cpu_count()
+            a, dt = cpu_leg(args.ref_pop, args.gran, cores, 0)
+            line["cpu_baseline"] = {"value": a / dt, "unit": "attempts/s", "cores": cores, "kind": "port",
+                                    "sample": "pop %d of %d genomes x 3 sizes x 5 seeds, one pass, oracle port (WyRand stream)"
+                                              % (args.ref_pop, POP_C2), "seconds": dt}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -96,6 +96,7 @@ template <> struct Plane<1> {       // padded grid side <= 32: one u32 per row
     static __device__ __forceinline__ uint32_t bit(const uint32_t* p, uint32_t r, uint32_t c) { return (p[r] >> c) & 1u; }
     static __device__ __forceinline__ void flip(uint32_t* p, uint32_t r, uint32_t c) { p[r] ^= 1u << c; }
     static __device__ __forceinline__ void atom_or(uint32_t* p, uint32_t r, uint32_t c) { atomicOr(&p[r], 1u << c); }
+    static __device__ __forceinline__ void atom_xor(uint32_t* p, uint32_t r, uint32_t c) { atomicXor(&p[r], 1u << c); }
 };
 template <> struct Plane<2> {       // padded grid side <= 64: one u64 per row
     static __device__ __forceinline__ uint32_t win(const uint32_t* p, uint32_t r, uint32_t cm1) {
@@ -105,6 +106,7 @@ template <> struct Plane<2> {       // padded grid side <= 64: one u64 per row
     static __device__ __forceinline__ uint32_t bit(const uint32_t* p, uint32_t r, uint32_t c) { return (p[2 * r + (c >> 5)] >> (c & 31)) & 1u; }
     static __device__ __forceinline__ void flip(uint32_t* p, uint32_t r, uint32_t c) { p[2 * r + (c >> 5)] ^= 1u << (c & 31); }
     static __device__ __forceinline__ void atom_or(uint32_t* p, uint32_t r, uint32_t c) { atomicOr(&p[2 * r + (c >> 5)], 1u << (c & 31)); }
+    static __device__ __forceinline__ void atom_xor(uint32_t* p, uint32_t r, uint32_t c) { atomicXor(&p[2 * r + (c >> 5)], 1u << (c & 31)); }
 };
 
 template <int RW>
@@ -222,18 +224,23 @@ __device__ __forceinline__ uint32_t threshold(const Lat& L, const Geo& g, uint32
     }
 }
 
-// --- commit of lane f's accepted proposal; called by ALL lanes with f's data broadcast -----------------
+// --- commit of lane f's accepted proposal ----------------------------------------------------------
+// AGG / COAT / LOCO: lane f alone flips its two cells in both planes (fire-and-forget shared atomics) and
+// rewrites its position.  SEP: a swap needs the partner's index (the reference's
+// participants.iter().position scan, separation.rs:302), found by a warp-wide scan, so every lane takes
+// part with lane f's data broadcast.
 template <int BEH, int RW>
 __device__ __forceinline__ void commit(const Lat& L, const Geo& g, uint32_t lane, uint32_t f,
-                                       uint32_t idxf, uint32_t sf, uint32_t tf, uint32_t kindf) {
-    uint32_t sr = sf & 0xff, sc = sf >> 8, tr = tf & 0xff, tc = tf >> 8;
+                                       uint32_t idx, uint32_t s, uint32_t t, uint32_t kind) {
     if (BEH == SEP) {
-        uint32_t col = sep_colour(g, idxf);
+        const uint32_t idxf = __shfl_sync(0xffffffffu, idx, f);
+        const uint32_t sf = __shfl_sync(0xffffffffu, s, f);
+        const uint32_t tf = __shfl_sync(0xffffffffu, t, f);
+        const uint32_t kindf = __shfl_sync(0xffffffffu, kind, f);
+        const uint32_t col = sep_colour(g, idxf);
         uint32_t partner = 0xffffffffu;
-        uint32_t x = col;                                    // bits to flip at both cells
+        uint32_t x = col;                                    // colour bits to flip at both cells
         if (kindf == 2) {
-            // swap: find the partner's index (the reference's participants.iter().position scan,
-            // separation.rs:302) with a warp-wide scan; effective swaps are ~0.3 % of attempts
             for (uint32_t base = 0; base < g.n; base += 32) {
                 uint32_t i = base + lane;
                 uint32_t hit = __ballot_sync(0xffffffffu, i < g.n && L.pos[i] == tf);
@@ -242,6 +249,7 @@ __device__ __forceinline__ void commit(const Lat& L, const Geo& g, uint32_t lane
             x = col ^ sep_colour(g, partner);
         }
         if (lane == f) {
+            const uint32_t sr = sf & 0xff, sc = sf >> 8, tr = tf & 0xff, tc = tf >> 8;
             if (x & 1) { Plane<RW>::flip(L.p0, sr, sc); Plane<RW>::flip(L.p0, tr, tc); }
             if (x & 2) { Plane<RW>::flip(L.p1, sr, sc); Plane<RW>::flip(L.p1, tr, tc); }
             L.pos[idxf] = (uint16_t)tf;
@@ -249,60 +257,46 @@ __device__ __forceinline__ void commit(const Lat& L, const Geo& g, uint32_t lane
         }
     } else {
         if (lane == f) {
-            if (BEH == LOCO) {                               // locomotion.rs:344-519, net effect (see oracle)
+            const uint32_t sr = s & 0xff, sc = s >> 8, tr = t & 0xff, tc = t >> 8;
+            if (BEH == LOCO) {                               // locomotion.rs:344-519, net effect
                 int a = (int)g.a, sx = (int)sr - 1, sy = (int)sc - 1, tx = (int)tr - 1, ty = (int)tc - 1;
                 uint32_t cur = loco_sense(L.light, g.orient, a, sx, sy);
                 uint32_t fut = loco_sense(L.light, g.orient, a, tx, ty);
                 if (cur) L.light[loco_beam(g.orient, a, sx, sy)] = (uint16_t)(sx | (sy << 8));
                 if (fut) L.light[loco_beam(g.orient, a, tx, ty)] = (uint16_t)(tx | (ty << 8));
             }
-            Plane<RW>::flip(L.p0, sr, sc); Plane<RW>::flip(L.p0, tr, tc);
-            Plane<RW>::flip(L.p1, sr, sc); Plane<RW>::flip(L.p1, tr, tc);
-            L.pos[idxf] = (uint16_t)tf;
+            Plane<RW>::atom_xor(L.p0, sr, sc); Plane<RW>::atom_xor(L.p0, tr, tc);
+            Plane<RW>::atom_xor(L.p1, sr, sc); Plane<RW>::atom_xor(L.p1, tr, tc);
+            L.pos[idx] = (uint16_t)t;
         }
     }
     __syncwarp();
 }
 
-// --- resolve one speculative batch -----------------------------------------------------------------
-// `active` lanes hold consecutive chain steps in lane order; `eff` lanes want to change the state.
-// Commits in order, cutting the batch at the first lane whose evaluation a commit invalidated.
-// Returns the lane bound R: active lanes < R are retired.  ncommit counts committed moves.
-template <int BEH, int RW>
-__device__ __forceinline__ uint32_t resolve(const Lat& L, const Geo& g, uint32_t lane, bool active, bool eff,
-                                            uint32_t idx, uint32_t s, uint32_t t, uint32_t kind, uint32_t& ncommit) {
-    uint32_t A = __ballot_sync(0xffffffffu, eff);
-    uint32_t R = 32;
-    while (A) {
-        uint32_t f = __ffs(A) - 1;
-        uint32_t idxf = __shfl_sync(0xffffffffu, idx, f);
-        uint32_t sf = __shfl_sync(0xffffffffu, s, f);
-        uint32_t tf = __shfl_sync(0xffffffffu, t, f);
-        uint32_t kindf = (BEH == SEP) ? __shfl_sync(0xffffffffu, kind, f) : 1u;
-        commit<BEH, RW>(L, g, lane, f, idxf, sf, tf, kindf);
-        ++ncommit;
-        bool cf = false;
-        if (active && lane > f && lane < R) {
-            if (kind == 0) {
-                cf = (s == sf) | (s == tf) | (t == sf) | (t == tf);
-            } else {
-                cf = adj_or_eq(sf, s) | adj_or_eq(sf, t) | adj_or_eq(tf, s) | adj_or_eq(tf, t);
-                if (BEH == LOCO) {                           // the light table is part of the read set
-                    int a = (int)g.a;
-                    int b1 = loco_beam(g.orient, a, (int)(sf & 0xff) - 1, (int)(sf >> 8) - 1);
-                    int b2 = loco_beam(g.orient, a, (int)(tf & 0xff) - 1, (int)(tf >> 8) - 1);
-                    int bs = loco_beam(g.orient, a, (int)(s & 0xff) - 1, (int)(s >> 8) - 1);
-                    int bt = loco_beam(g.orient, a, (int)(t & 0xff) - 1, (int)(t >> 8) - 1);
-                    cf |= (bs == b1) | (bs == b2) | (bt == b1) | (bt == b2);
-                }
-            }
-        }
-        uint32_t C = __ballot_sync(0xffffffffu, cf);
-        if (C) R = __ffs(C) - 1;
-        A &= ~((2u << f) - 1u);
-        A &= lowmask(R);
+// --- conflict test between a lane's evaluation and a committed move -----------------------------------
+// A lane's read set is the cells adjacent-or-equal to its s or t; a commit writes sf and tf.  With
+// m = s + t (the doubled midpoint, per 8-bit field) any true conflict has |m - mf| <= 4 in both fields
+// (2|x - y| + |delta| + |delta_f| with |x - y| <= 1), so the box test below is a cheap superset; a false
+// positive only costs a re-evaluation.  Fields are spread to 16 bits so the biased subtraction cannot
+// borrow across them when in range.
+__device__ __forceinline__ uint32_t spread16(uint32_t m) { return __byte_perm(m, 0, 0x4140); }
+__device__ __forceinline__ bool box_conflict(uint32_t m32, uint32_t mf32) {
+    uint32_t x = m32 + 0x00040004u - mf32;
+    uint32_t y = x | (x + 0x00070007u);
+    return (y & 0xfff0fff0u) == 0u;
+}
+template <int BEH>
+__device__ __forceinline__ bool conflicts(const Geo& g, uint32_t s, uint32_t t, uint32_t m32, uint32_t sf, uint32_t tf, uint32_t mf32) {
+    bool cf = box_conflict(m32, mf32);
+    if (BEH == LOCO) {                                       // the light table is part of the read set
+        int a = (int)g.a;
+        int b1 = loco_beam(g.orient, a, (int)(sf & 0xff) - 1, (int)(sf >> 8) - 1);
+        int b2 = loco_beam(g.orient, a, (int)(tf & 0xff) - 1, (int)(tf >> 8) - 1);
+        int bs = loco_beam(g.orient, a, (int)(s & 0xff) - 1, (int)(s >> 8) - 1);
+        int bt = loco_beam(g.orient, a, (int)(t & 0xff) - 1, (int)(t >> 8) - 1);
+        cf |= (bs == b1) | (bs == b2) | (bt == b1) | (bt == b2);
     }
-    return R;
+    return cf;
 }
 
 // --- initial configuration ---------------------------------------------------------------------------
@@ -482,47 +476,68 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
 
     const uint64_t steps = in.steps, ms = in.move_seed;
     const uint32_t n = g.n;
-    uint64_t k = 0, nposs = 0;
-    uint32_t ncommit = 0;
+    uint64_t nposs = 0;                                      // per lane
+    uint32_t ncommit = 0;                                    // per lane
 
     if (MODE == MODE_FAST) {
+        // Every batch retires 32 consecutive steps.  Lanes evaluate their proposal against the current
+        // lattice; the lowest accepted lane commits; later lanes whose read set may have been touched
+        // re-evaluate (same random numbers, new state) before the next commit is chosen.  The retired
+        // sequence is exactly the sequential chain.
         const uint32_t key = (uint32_t)ms, khi = (uint32_t)(ms >> 32);
-        while (k < steps) {
-            uint64_t rem = steps - k;
-            uint64_t st = k + lane;
+        const uint64_t nbatch = (steps + 31) >> 5;
+        for (uint64_t b = 0; b < nbatch; ++b) {
+            const uint64_t st = (b << 5) + lane;
             uint32_t r0, r1;
             philox2x32_10((uint32_t)st, (uint32_t)(st >> 32) ^ khi, key, r0, r1);
-            uint32_t idx = __umulhi(r0, n);
-            uint64_t m6 = (uint64_t)r1 * 6u;
-            uint32_t d = (uint32_t)(m6 >> 32), plo = (uint32_t)m6;
-            uint32_t s, t, kind;
-            probe<BEH, RW>(L, idx, d, s, t, kind);
-            bool active = (uint64_t)lane < rem;
-            bool poss = active && kind != 0;
-            bool eff = false;
-            if (poss) {
-                bool noop;
-                uint32_t thr = threshold<BEH, RW>(L, g, idx, d, s, t, kind, noop);
-                eff = (__umulhi(plo, 1000u) < thr) && !noop;
+            const uint32_t idx = __umulhi(r0, n);
+            const uint64_t m6 = (uint64_t)r1 * 6u;
+            const uint32_t d = (uint32_t)(m6 >> 32);
+            const uint32_t pd = __umulhi((uint32_t)m6, 1000u);
+            const bool active = st < steps;
+            bool need = active, eff = false, poss = false;
+            uint32_t s = 0, t = 0, kind = 0, m32 = 0, done = 0;
+            for (;;) {
+                if (need) {
+                    probe<BEH, RW>(L, idx, d, s, t, kind);
+                    poss = kind != 0;
+                    eff = false;
+                    if (poss) {
+                        bool noop;
+                        uint32_t thr = threshold<BEH, RW>(L, g, idx, d, s, t, kind, noop);
+                        eff = (pd < thr) && !noop;
+                    }
+                    m32 = spread16(s + t);
+                }
+                const uint32_t A = __ballot_sync(0xffffffffu, eff) & ~lowmask(done);
+                if (!A) break;
+                const uint32_t f = __ffs(A) - 1;
+                commit<BEH, RW>(L, g, lane, f, idx, s, t, kind);
+                const uint32_t mf32 = __shfl_sync(0xffffffffu, m32, f);
+                uint32_t sf = 0, tf = 0;
+                if (BEH == LOCO) { sf = __shfl_sync(0xffffffffu, s, f); tf = __shfl_sync(0xffffffffu, t, f); }
+                need = active && lane > f && conflicts<BEH>(g, s, t, m32, sf, tf, mf32);
+                if (lane == f) ++ncommit;
+                done = f + 1;
             }
-            uint32_t pm = __ballot_sync(0xffffffffu, poss);
-            uint32_t R = resolve<BEH, RW>(L, g, lane, active, eff, idx, s, t, poss ? kind : 0u, ncommit);
-            uint32_t lim = rem < (uint64_t)R ? (uint32_t)rem : R;
-            nposs += __popc(pm & lowmask(lim));
-            k += lim;
+            nposs += poss;
         }
     } else {
-        uint64_t cbase = 0;                                  // thread-local draws consumed so far
+        // Verification mode: the number of draws a step consumes (2 if blocked, 3 if possible) decides
+        // where the next step starts in the WyRand chain, so lanes evaluate both alignments and a
+        // warp-uniform walk over the "possible" ballots picks the real ones.  A commit that flips a later
+        // lane's possible-ness invalidates that alignment: the batch is cut there.
+        uint64_t k = 0, cbase = 0;                           // steps retired, thread-local draws consumed
         while (k < steps) {
-            uint64_t rem = steps - k;
+            const uint64_t rem = steps - k;
             // raw draws cbase + 2l + 1 (even slot) and cbase + 2l + 2 (odd slot)
             const uint64_t kE = cbase + 2 * lane + 1, kO = kE + 1;
-            uint64_t rE = wy_draw(ms, kE), rO = wy_draw(ms, kO);
-            uint64_t nE = __shfl_down_sync(0xffffffffu, rE, 1);
-            uint32_t nO32 = __shfl_down_sync(0xffffffffu, (uint32_t)rO, 1);
+            const uint64_t rE = wy_draw(ms, kE), rO = wy_draw(ms, kO);
+            const uint64_t nE = __shfl_down_sync(0xffffffffu, rE, 1);
+            const uint32_t nO32 = __shfl_down_sync(0xffffffffu, (uint32_t)rO, 1);
             // a step starting in the even slot uses (rE, rO, next rE); in the odd slot (rO, next rE, next rO)
-            uint32_t idxE = wy_mod_u64(rE, n, ms, kE), dE = wy_mod_u64(rO, 6, ms, kO);
-            uint32_t idxO = wy_mod_u64(rO, n, ms, kO), dO = wy_mod_u64(nE, 6, ms, kO + 1);
+            const uint32_t idxE = wy_mod_u64(rE, n, ms, kE), dE = wy_mod_u64(rO, 6, ms, kO);
+            const uint32_t idxO = wy_mod_u64(rO, n, ms, kO), dO = wy_mod_u64(nE, 6, ms, kO + 1);
             uint32_t sE, tE, kindE, sO, tO, kindO;
             probe<BEH, RW>(L, idxE, dE, sE, tE, kindE);
             probe<BEH, RW>(L, idxO, dO, sO, tO, kindO);
@@ -530,35 +545,74 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
             // which slots start a real step: a blocked step consumes 2 draws, a possible one 3
             uint32_t realE = 0, realO = 0, l = 0, par = 0;
             while (l < 31) {
-                uint32_t m = ((par ? PO : PE) >> l) & ((1u << (31 - l)) - 1u);
-                uint32_t upto = m ? l + (uint32_t)__ffs(m) - 1 : 30u;
+                uint32_t mm = ((par ? PO : PE) >> l) & ((1u << (31 - l)) - 1u);
+                uint32_t upto = mm ? l + (uint32_t)__ffs(mm) - 1 : 30u;
                 uint32_t mask = ((2u << upto) - 1u) & ~((1u << l) - 1u);
                 if (par) realO |= mask; else realE |= mask;
-                if (!m) { l = 31; break; }
+                if (!mm) { l = 31; break; }
                 if (par) { l = upto + 2; par = 0; } else { l = upto + 1; par = 1; }
             }
             const uint32_t q_end = 2 * l + par;
             const bool myO = (realO >> lane) & 1u, myE = (realE >> lane) & 1u;
             const uint32_t ord = __popc((realE | realO) & lowmask(lane));
             const bool active = (myE || myO) && (uint64_t)ord < rem;
-            uint32_t idx = myO ? idxO : idxE, d = myO ? dO : dE, s = myO ? sO : sE, t = myO ? tO : tE;
-            uint32_t kind = myO ? kindO : kindE;
-            bool poss = active && kind != 0;
+            const uint32_t idx = myO ? idxO : idxE, d = myO ? dO : dE;
+            uint32_t s = myO ? sO : sE, t = myO ? tO : tE, kind = myO ? kindO : kindE;
+            const bool poss = active && kind != 0;
             bool eff = false;
+            uint32_t pd = 0;
             if (poss) {
                 bool noop;
                 uint32_t thr = threshold<BEH, RW>(L, g, idx, d, s, t, kind, noop);
-                uint32_t pd = wy_mod_1000(myO ? nO32 : (uint32_t)nE, ms, (myO ? kO : kE) + 2);
+                pd = wy_mod_1000(myO ? nO32 : (uint32_t)nE, ms, (myO ? kO : kE) + 2);
                 eff = (pd < thr) && !noop;
             }
-            uint32_t pm = __ballot_sync(0xffffffffu, poss);
-            uint32_t am = __ballot_sync(0xffffffffu, active);
-            uint32_t R = resolve<BEH, RW>(L, g, lane, active, eff, idx, s, t, poss ? kind : 0u, ncommit);
-            nposs += __popc(pm & lowmask(R));
+            uint32_t m32 = spread16(s + t);
+            const uint32_t pm = __ballot_sync(0xffffffffu, poss), am = __ballot_sync(0xffffffffu, active);
+            uint32_t R = 32, done = 0;
+            for (;;) {
+                const uint32_t A = __ballot_sync(0xffffffffu, eff) & ~lowmask(done) & lowmask(R);
+                if (!A) break;
+                const uint32_t f = __ffs(A) - 1;
+                commit<BEH, RW>(L, g, lane, f, idx, s, t, kind);
+                const uint32_t mf32 = __shfl_sync(0xffffffffu, m32, f);
+                uint32_t sf = 0, tf = 0;
+                if (BEH == LOCO) { sf = __shfl_sync(0xffffffffu, s, f); tf = __shfl_sync(0xffffffffu, t, f); }
+                const bool need = active && lane > f && lane < R && conflicts<BEH>(g, s, t, m32, sf, tf, mf32);
+                bool changed = false;
+                if (need) {
+                    uint32_t k2;
+                    probe<BEH, RW>(L, idx, d, s, t, k2);
+                    if ((k2 != 0) != poss) changed = true;
+                    else {
+                        kind = k2;
+                        if (poss) {
+                            bool noop;
+                            uint32_t thr = threshold<BEH, RW>(L, g, idx, d, s, t, kind, noop);
+                            eff = (pd < thr) && !noop;
+                        }
+                        m32 = spread16(s + t);
+                    }
+                }
+                const uint32_t C = __ballot_sync(0xffffffffu, changed);
+                if (C) R = __ffs(C) - 1;
+                if (lane == f) ++ncommit;
+                done = f + 1;
+            }
+            nposs += (poss && lane < R) ? 1u : 0u;
             k += __popc(am & lowmask(R));
+            (void)pm;
             if (R < 32) cbase += 2 * R + __shfl_sync(0xffffffffu, (uint32_t)myO, R);   // the cut lane restarts the next batch
             else cbase += q_end;
         }
+    }
+    {
+        // per-lane counters -> warp totals
+        uint32_t lo = __reduce_add_sync(0xffffffffu, (uint32_t)(nposs & 0xffffffu));
+        uint32_t mid = __reduce_add_sync(0xffffffffu, (uint32_t)((nposs >> 24) & 0xffffffu));
+        uint32_t hi = __reduce_add_sync(0xffffffffu, (uint32_t)(nposs >> 48));
+        nposs = (uint64_t)lo + ((uint64_t)mid << 24) + ((uint64_t)hi << 48);
+        ncommit = __reduce_add_sync(0xffffffffu, ncommit);
     }
 
     uint32_t i0, i1;

@@ -31,9 +31,12 @@ def probe(name, beh, P, sizes, seeds, mode, steps=0, reps=2):
 
 
 which = sys.argv[1:] or ["c2", "c5", "sep", "coat", "loco"]
-for mode in (1, 0):
+modes = [m for m, nm in ((1, "fast"), (0, "verify")) if nm in which] or [1, 0]
+for mode in modes:
     if "c2" in which:
         probe("C2 agg pop50 x3 sizes x5 seeds", E.AGG, 50, [(6, 4), (10, 7), (13, 9)], [1, 2, 3, 4, 5], mode)
+    if "c5s" in which:
+        probe("agg (13,9) 20000 inst x 2e5 steps", E.AGG, 1, [(13, 9)], list(range(1, 20001)), mode, steps=200000, reps=1)
     if "c5" in which:
         probe("agg (13,9) 20000 inst x 2e5 steps", E.AGG, 1, [(13, 9)], list(range(1, 20001)), mode, steps=200000)
         probe("agg (13,9) 100000 inst x 1e5 steps", E.AGG, 1, [(13, 9)], list(range(1, 100001)), mode, steps=100000)
