@@ -35,6 +35,8 @@ modes = [m for m, nm in ((1, "fast"), (0, "verify")) if nm in which] or [1, 0]
 for mode in modes:
     if "c2" in which:
         probe("C2 agg pop50 x3 sizes x5 seeds", E.AGG, 50, [(6, 4), (10, 7), (13, 9)], [1, 2, 3, 4, 5], mode)
+    if "c2s" in which:
+        probe("agg (13,9) pop50 x5 seeds 2e6 steps", E.AGG, 50, [(13, 9)], [1, 2, 3, 4, 5], mode, steps=2000000, reps=1)
     if "c5s" in which:
         probe("agg (13,9) 20000 inst x 2e5 steps", E.AGG, 1, [(13, 9)], list(range(1, 20001)), mode, steps=200000, reps=1)
     if "c5" in which:
