@@ -462,6 +462,80 @@ __device__ __forceinline__ void fitness(const KParams& P, const Lat& L, const Ge
     i1 = __reduce_add_sync(0xffffffffu, s1);
 }
 
+// --- evaluation of one proposal against the current lattice -------------------------------------------
+struct Prop {
+    uint32_t idx, d, pd;            // particle, direction, probability draw (0..999): fixed for the step
+    uint32_t s, t, kind, m32;       // evaluated: source, target, 0 blocked / 1 move / 2 swap, spread midpoint
+    bool poss, eff;                 // target enterable; would change the state
+};
+template <int BEH, int RW>
+__device__ __forceinline__ void evaluate(const Lat& L, const Geo& g, Prop& p) {
+    probe<BEH, RW>(L, p.idx, p.d, p.s, p.t, p.kind);
+    p.poss = p.kind != 0;
+    p.eff = false;
+    if (p.poss) {
+        bool noop;
+        uint32_t thr = threshold<BEH, RW>(L, g, p.idx, p.d, p.s, p.t, p.kind, noop);
+        p.eff = (p.pd < thr) && !noop;
+    }
+    p.m32 = spread16(p.s + p.t);
+}
+
+// --- commit / repair rounds of one speculative batch ---------------------------------------------------
+// On entry every active lane holds a proposal evaluated against the current lattice; lane order = chain
+// order.  Each round: (1) every lane tests itself against every pending accepted lane before it (the
+// "dirty" matrix, one shuffle per accepted lane); (2) all accepted lanes in front of the first dirty lane
+// commit at once — none of their read sets was touched, and their moves are pairwise far apart;
+// (3) lanes dirtied by a committed move re-evaluate with their own (fixed) random numbers.  The retired
+// sequence is exactly the sequential chain.  VERIFY: a re-evaluation that flips a lane's possible-ness
+// changes how many draws that step consumes, so the batch is cut at that lane (returned bound R).
+template <int BEH, int RW, bool VERIFY>
+__device__ __forceinline__ uint32_t resolve_batch(const Lat& L, const Geo& g, uint32_t lane, bool active, Prop& p, uint32_t& ncommit) {
+    uint32_t R = 32;
+    for (;;) {
+        uint32_t A = __ballot_sync(0xffffffffu, p.eff);
+        if (VERIFY) A &= lowmask(R);
+        if (!A) break;
+        uint32_t dirtyBy = 0, Ai = A;
+        do {
+            const uint32_t e = __ffs(Ai) - 1;
+            Ai &= Ai - 1;
+            const uint32_t mf32 = __shfl_sync(0xffffffffu, p.m32, e);
+            uint32_t sf = 0, tf = 0;
+            if (BEH == LOCO) { sf = __shfl_sync(0xffffffffu, p.s, e); tf = __shfl_sync(0xffffffffu, p.t, e); }
+            if (lane > e && conflicts<BEH>(g, p.s, p.t, p.m32, sf, tf, mf32)) dirtyBy |= 1u << e;
+        } while (Ai);
+        uint32_t D = __ballot_sync(0xffffffffu, active && dirtyBy != 0);
+        if (VERIFY) D &= lowmask(R);
+        const uint32_t bnd = D ? (uint32_t)__ffs(D) - 1 : 32u;
+        const uint32_t C = A & lowmask(bnd);                 // never empty: the first accepted lane cannot be dirty
+        if (BEH == SEP) {
+            uint32_t Ci = C;
+            do {
+                const uint32_t e = __ffs(Ci) - 1;
+                Ci &= Ci - 1;
+                commit<BEH, RW>(L, g, lane, e, p.idx, p.s, p.t, p.kind);
+            } while (Ci);
+        } else {
+            commit<BEH, RW>(L, g, lane, ((C >> lane) & 1u) ? lane : 32u, p.idx, p.s, p.t, p.kind);
+        }
+        if ((C >> lane) & 1u) { p.eff = false; ++ncommit; }
+        if (!D) break;                                       // nothing dirtied: every accepted lane has committed
+        const bool need = active && lane >= bnd && (dirtyBy & C) != 0 && (!VERIFY || lane < R);
+        bool changed = false;
+        if (need) {
+            const bool was = p.poss;
+            evaluate<BEH, RW>(L, g, p);
+            if (VERIFY && p.poss != was) { changed = true; p.eff = false; }
+        }
+        if (VERIFY) {
+            const uint32_t X = __ballot_sync(0xffffffffu, changed);
+            if (X) R = min(R, (uint32_t)__ffs(X) - 1);
+        }
+    }
+    return R;
+}
+
 // --- one instance, start to finish ------------------------------------------------------------------
 template <int BEH, int RW, int MODE>
 __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, const Instance& in, uint32_t lane) {
@@ -480,47 +554,35 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
     uint32_t ncommit = 0;                                    // per lane
 
     if (MODE == MODE_FAST) {
-        // Every batch retires 32 consecutive steps.  Lanes evaluate their proposal against the current
-        // lattice; the lowest accepted lane commits; later lanes whose read set may have been touched
-        // re-evaluate (same random numbers, new state) before the next commit is chosen.  The retired
-        // sequence is exactly the sequential chain.
+        // Every batch retires 32 consecutive steps; the random numbers of batch b+1 do not depend on the
+        // lattice, so they are drawn while batch b's shared-memory loads are in flight.
         const uint32_t key = (uint32_t)ms, khi = (uint32_t)(ms >> 32);
-        const uint64_t nbatch = (steps + 31) >> 5;
-        for (uint64_t b = 0; b < nbatch; ++b) {
-            const uint64_t st = (b << 5) + lane;
+        const uint64_t nfull = steps >> 5;
+        const uint32_t tail = (uint32_t)steps & 31u;
+        auto draw = [&](uint64_t st, Prop& q) {
             uint32_t r0, r1;
             philox2x32_10((uint32_t)st, (uint32_t)(st >> 32) ^ khi, key, r0, r1);
-            const uint32_t idx = __umulhi(r0, n);
+            q.idx = __umulhi(r0, n);
             const uint64_t m6 = (uint64_t)r1 * 6u;
-            const uint32_t d = (uint32_t)(m6 >> 32);
-            const uint32_t pd = __umulhi((uint32_t)m6, 1000u);
-            const bool active = st < steps;
-            bool need = active, eff = false, poss = false;
-            uint32_t s = 0, t = 0, kind = 0, m32 = 0, done = 0;
-            for (;;) {
-                if (need) {
-                    probe<BEH, RW>(L, idx, d, s, t, kind);
-                    poss = kind != 0;
-                    eff = false;
-                    if (poss) {
-                        bool noop;
-                        uint32_t thr = threshold<BEH, RW>(L, g, idx, d, s, t, kind, noop);
-                        eff = (pd < thr) && !noop;
-                    }
-                    m32 = spread16(s + t);
-                }
-                const uint32_t A = __ballot_sync(0xffffffffu, eff) & ~lowmask(done);
-                if (!A) break;
-                const uint32_t f = __ffs(A) - 1;
-                commit<BEH, RW>(L, g, lane, f, idx, s, t, kind);
-                const uint32_t mf32 = __shfl_sync(0xffffffffu, m32, f);
-                uint32_t sf = 0, tf = 0;
-                if (BEH == LOCO) { sf = __shfl_sync(0xffffffffu, s, f); tf = __shfl_sync(0xffffffffu, t, f); }
-                need = active && lane > f && conflicts<BEH>(g, s, t, m32, sf, tf, mf32);
-                if (lane == f) ++ncommit;
-                done = f + 1;
-            }
-            nposs += poss;
+            q.d = (uint32_t)(m6 >> 32);
+            q.pd = __umulhi((uint32_t)m6, 1000u);
+        };
+        Prop cur;
+        draw((uint64_t)lane, cur);
+        for (uint64_t b = 0; b < nfull; ++b) {
+            Prop nxt;
+            draw(((b + 1) << 5) + lane, nxt);
+            evaluate<BEH, RW>(L, g, cur);
+            resolve_batch<BEH, RW, false>(L, g, lane, true, cur, ncommit);
+            nposs += cur.poss;
+            cur.idx = nxt.idx; cur.d = nxt.d; cur.pd = nxt.pd;
+        }
+        if (tail) {
+            const bool active = lane < tail;
+            cur.s = cur.t = cur.kind = cur.m32 = 0; cur.poss = cur.eff = false;
+            if (active) evaluate<BEH, RW>(L, g, cur);
+            resolve_batch<BEH, RW, false>(L, g, lane, active, cur, ncommit);
+            nposs += (active && cur.poss) ? 1u : 0u;
         }
     } else {
         // Verification mode: the number of draws a step consumes (2 if blocked, 3 if possible) decides
@@ -556,52 +618,23 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
             const bool myO = (realO >> lane) & 1u, myE = (realE >> lane) & 1u;
             const uint32_t ord = __popc((realE | realO) & lowmask(lane));
             const bool active = (myE || myO) && (uint64_t)ord < rem;
-            const uint32_t idx = myO ? idxO : idxE, d = myO ? dO : dE;
-            uint32_t s = myO ? sO : sE, t = myO ? tO : tE, kind = myO ? kindO : kindE;
-            const bool poss = active && kind != 0;
-            bool eff = false;
-            uint32_t pd = 0;
-            if (poss) {
+            Prop p;
+            p.idx = myO ? idxO : idxE; p.d = myO ? dO : dE;
+            p.s = myO ? sO : sE; p.t = myO ? tO : tE; p.kind = active ? (myO ? kindO : kindE) : 0u;
+            p.poss = p.kind != 0;
+            p.eff = false;
+            p.pd = 0;
+            if (p.poss) {
                 bool noop;
-                uint32_t thr = threshold<BEH, RW>(L, g, idx, d, s, t, kind, noop);
-                pd = wy_mod_1000(myO ? nO32 : (uint32_t)nE, ms, (myO ? kO : kE) + 2);
-                eff = (pd < thr) && !noop;
+                uint32_t thr = threshold<BEH, RW>(L, g, p.idx, p.d, p.s, p.t, p.kind, noop);
+                p.pd = wy_mod_1000(myO ? nO32 : (uint32_t)nE, ms, (myO ? kO : kE) + 2);
+                p.eff = (p.pd < thr) && !noop;
             }
-            uint32_t m32 = spread16(s + t);
-            const uint32_t pm = __ballot_sync(0xffffffffu, poss), am = __ballot_sync(0xffffffffu, active);
-            uint32_t R = 32, done = 0;
-            for (;;) {
-                const uint32_t A = __ballot_sync(0xffffffffu, eff) & ~lowmask(done) & lowmask(R);
-                if (!A) break;
-                const uint32_t f = __ffs(A) - 1;
-                commit<BEH, RW>(L, g, lane, f, idx, s, t, kind);
-                const uint32_t mf32 = __shfl_sync(0xffffffffu, m32, f);
-                uint32_t sf = 0, tf = 0;
-                if (BEH == LOCO) { sf = __shfl_sync(0xffffffffu, s, f); tf = __shfl_sync(0xffffffffu, t, f); }
-                const bool need = active && lane > f && lane < R && conflicts<BEH>(g, s, t, m32, sf, tf, mf32);
-                bool changed = false;
-                if (need) {
-                    uint32_t k2;
-                    probe<BEH, RW>(L, idx, d, s, t, k2);
-                    if ((k2 != 0) != poss) changed = true;
-                    else {
-                        kind = k2;
-                        if (poss) {
-                            bool noop;
-                            uint32_t thr = threshold<BEH, RW>(L, g, idx, d, s, t, kind, noop);
-                            eff = (pd < thr) && !noop;
-                        }
-                        m32 = spread16(s + t);
-                    }
-                }
-                const uint32_t C = __ballot_sync(0xffffffffu, changed);
-                if (C) R = __ffs(C) - 1;
-                if (lane == f) ++ncommit;
-                done = f + 1;
-            }
-            nposs += (poss && lane < R) ? 1u : 0u;
+            p.m32 = spread16(p.s + p.t);
+            const uint32_t am = __ballot_sync(0xffffffffu, active);
+            const uint32_t R = resolve_batch<BEH, RW, true>(L, g, lane, active, p, ncommit);
+            nposs += (p.poss && lane < R) ? 1u : 0u;
             k += __popc(am & lowmask(R));
-            (void)pm;
             if (R < 32) cbase += 2 * R + __shfl_sync(0xffffffffu, (uint32_t)myO, R);   // the cut lane restarts the next batch
             else cbase += q_end;
         }

@@ -7,11 +7,11 @@ import numpy as np
 sys.path.insert(0, ".")
 import evosops_b200 as E
 
-rng = np.random.default_rng(1)
 ctx = E.Context()
 
 
 def probe(name, beh, P, sizes, seeds, mode, steps=0, reps=2):
+    rng = np.random.default_rng(abs(hash((beh, P))) % (2 ** 31))
     gs = rng.integers(0, 11, size=(P, E.GENOME_LEN[beh]), dtype=np.uint8)
     tsz = [s for s in sizes for _ in seeds]
     tsd = [sd for _ in sizes for sd in seeds]
