@@ -206,10 +206,13 @@ void layout_group(Group& g, int beh, uint32_t max_pg, uint32_t max_n) {
     g.plane_words = ((max_pg * (uint32_t)g.rw) + 1u) & ~1u;     // keep 64-bit rows 8-byte aligned
     g.pos_words = ((max_n + 1) / 2 + 1u) & ~1u;
     uint32_t thr_words = (uint32_t)genome_len(beh) / 2;
+    // every plane carries one guard row above row 0 and one below the last row (3x3 windows of cells in
+    // the padding ring read them); off_p* point at row 0
+    const uint32_t guard = (uint32_t)g.rw, span = g.plane_words + 2 * guard;
     uint32_t off = 0;
-    g.off_p0 = off; off += g.plane_words;
-    g.off_p1 = off; off += g.plane_words;
-    g.off_p2 = off; if (three) off += g.plane_words;
+    g.off_p0 = off + guard; off += span;
+    g.off_p1 = off + guard; off += span;
+    g.off_p2 = off + guard; if (three) off += span;
     g.off_pos = off; off += g.pos_words;
     g.off_thr = off; off += thr_words;
     g.off_aux = off; if (beh == SOPS_LOCO) off += SOPS_LIGHT_WORDS;

@@ -9,11 +9,12 @@
 // Design:
 //   * The lattice lives in shared memory as bit planes (one 32- or 64-bit word per padded row), the
 //     particle list as packed u16 (row+1 | (col+1) << 8), the genome as u16 acceptance thresholds.
-//   * The Markov chain is strictly sequential, but only ~0.3-8 % of proposals change the state.  The 32
-//     lanes therefore evaluate the next 32 proposals SPECULATIVELY against the current lattice; the
-//     first accepted proposal is committed, later lanes stay valid unless their read set touches the
-//     written cells, and the batch is cut at the first such conflict.  The retired sequence is
-//     exactly the sequential one.
+//   * The Markov chain is strictly sequential, but only ~0.3-15 % of proposals change the state.  The 32
+//     lanes therefore evaluate the next 32 proposals SPECULATIVELY against the current lattice and keep
+//     what they read — the two 3x3 bit windows around source and target — in registers.  The lowest
+//     accepted lane commits; every later lane patches its windows with the two flipped cells (pure
+//     register arithmetic, exact) and re-derives its decision; then the next accepted lane commits.
+//     All 32 steps retire every batch and the retired sequence is exactly the sequential chain.
 //   * Both RNG modes are counter based: fast = Philox2x32-10 keyed per step; verify = the WyRand
 //     double chain, whose draw count per step (2 or 3) depends on the state — resolved per batch by a
 //     warp-uniform walk over the "possible" ballots.
@@ -33,7 +34,7 @@ struct Instance {                   // 40 bytes, built on the host, sorted by co
     uint64_t move_seed;
     uint64_t steps;
     uint32_t genome;                // genome index
-    uint32_t slot;                  // output slot (instance id q = g*T + t)
+    uint32_t slot;                  // output slot on this device
     uint32_t aux;                   // coat: element offset of this size's distance table
     uint8_t arena, layers, coat, orient;
 };
@@ -53,10 +54,11 @@ struct KParams {
     uint32_t dump_stride;
     uint32_t dump_slot0;            // first slot of this launch (dump rows are launch-relative)
     const uint16_t* coat_dist;      // coat: per-size G*G distance tables (0xFFFF = none)
-    // per-warp shared-memory layout, in 32-bit words
+    // per-warp shared-memory layout, in 32-bit words.  Each plane has one guard row above row 0 and one
+    // below row PG-1 (windows of cells in the padding ring read them); off_p* point at row 0.
     uint32_t words_per_warp;
     uint32_t off_p0, off_p1, off_p2, off_pos, off_thr, off_aux;
-    uint32_t plane_words, pos_words;
+    uint32_t plane_words, pos_words;    // plane_words: rows 0..PG-1 as dumped (without the guard rows)
 };
 
 #define SOPS_LIGHT_WORDS 32u        // 64 u16 beams (a <= 30 -> 2a+1 <= 61)
@@ -79,12 +81,9 @@ __host__ __device__ constexpr uint32_t dir_word(int d) {
     return dir_mid(d) | ((NB_MASK & ~dir_mid(d) & ~(1u << dir_bit(d))) << 9) |
            ((NB_MASK & ~dir_mid(d ^ 1) & ~(1u << dir_bit(d ^ 1))) << 18);
 }
-
 // packed position delta of direction d on (row | col << 8):  -1, +1, -256, +256, -257, +257
-__device__ __forceinline__ int dir_delta(uint32_t d) {
-    uint32_t h = d >> 1;
-    int mag = h ? (int)(255u + h) : 1;
-    return (d & 1) ? mag : -mag;
+__host__ __device__ constexpr int dir_delta(int d) {
+    return d == 0 ? -1 : d == 1 ? 1 : d == 2 ? -256 : d == 3 ? 256 : d == 4 ? -257 : 257;
 }
 
 __device__ __forceinline__ uint32_t lowmask(uint32_t r) { return r >= 32 ? 0xffffffffu : ((1u << r) - 1u); }
@@ -92,33 +91,34 @@ __device__ __forceinline__ uint32_t lowmask(uint32_t r) { return r >= 32 ? 0xfff
 // ------------------------------------------------------------------------------ bit planes ------
 template <int RW> struct Plane;
 template <> struct Plane<1> {       // padded grid side <= 32: one u32 per row
-    static __device__ __forceinline__ uint32_t win(const uint32_t* p, uint32_t r, uint32_t cm1) { return (p[r] >> cm1) & 7u; }
+    static __device__ __forceinline__ uint32_t win(const uint32_t* p, int r, uint32_t cm1) { return (p[r] >> (cm1 & 31u)) & 7u; }
     static __device__ __forceinline__ uint32_t bit(const uint32_t* p, uint32_t r, uint32_t c) { return (p[r] >> c) & 1u; }
-    static __device__ __forceinline__ void flip(uint32_t* p, uint32_t r, uint32_t c) { p[r] ^= 1u << c; }
     static __device__ __forceinline__ void atom_or(uint32_t* p, uint32_t r, uint32_t c) { atomicOr(&p[r], 1u << c); }
     static __device__ __forceinline__ void atom_xor(uint32_t* p, uint32_t r, uint32_t c) { atomicXor(&p[r], 1u << c); }
 };
 template <> struct Plane<2> {       // padded grid side <= 64: one u64 per row
-    static __device__ __forceinline__ uint32_t win(const uint32_t* p, uint32_t r, uint32_t cm1) {
+    static __device__ __forceinline__ uint32_t win(const uint32_t* p, int r, uint32_t cm1) {
         uint64_t w = *reinterpret_cast<const uint64_t*>(p + 2 * r);
-        return (uint32_t)(w >> cm1) & 7u;
+        return (uint32_t)(w >> (cm1 & 63u)) & 7u;
     }
     static __device__ __forceinline__ uint32_t bit(const uint32_t* p, uint32_t r, uint32_t c) { return (p[2 * r + (c >> 5)] >> (c & 31)) & 1u; }
-    static __device__ __forceinline__ void flip(uint32_t* p, uint32_t r, uint32_t c) { p[2 * r + (c >> 5)] ^= 1u << (c & 31); }
     static __device__ __forceinline__ void atom_or(uint32_t* p, uint32_t r, uint32_t c) { atomicOr(&p[2 * r + (c >> 5)], 1u << (c & 31)); }
     static __device__ __forceinline__ void atom_xor(uint32_t* p, uint32_t r, uint32_t c) { atomicXor(&p[2 * r + (c >> 5)], 1u << (c & 31)); }
 };
 
+// 3x3 window around padded cell (r, c); r-1 / r+1 may be a guard row, c-1 may be -1 (garbage bits that the
+// caller never uses: such a cell is statically blocked)
 template <int RW>
 __device__ __forceinline__ uint32_t win9(const uint32_t* p, uint32_t r, uint32_t c) {
-    return Plane<RW>::win(p, r - 1, c - 1) | (Plane<RW>::win(p, r, c - 1) << 3) | (Plane<RW>::win(p, r + 1, c - 1) << 6);
+    const int ri = (int)r;
+    return Plane<RW>::win(p, ri - 1, c - 1) | (Plane<RW>::win(p, ri, c - 1) << 3) | (Plane<RW>::win(p, ri + 1, c - 1) << 6);
 }
 
-// c adjacent-or-equal to x on the triangular lattice (packed positions)
-__device__ __forceinline__ bool adj_or_eq(uint32_t c, uint32_t x) {
-    int dr = (int)(c & 0xff) - (int)(x & 0xff);
-    int dc = (int)(c >> 8) - (int)(x >> 8);
-    return (unsigned)(dr + 1) <= 2u && (unsigned)(dc + 1) <= 2u && (unsigned)(dr - dc + 1) <= 2u;
+// window bit of cell x (packed) in the 3x3 window whose top-left cell is `org` (= centre - 0x0101); 0 if outside
+__device__ __forceinline__ uint32_t win_bit(uint32_t x, uint32_t org) {
+    const uint32_t v = x - org;                              // (dr + 1) | (dc + 1) << 8 when inside
+    const uint32_t m = ((1u << ((v >> 8) & 31u)) & 7u) << ((v & 3u) * 3u);   // row 3 lands above bit 8: ignored by every mask
+    return (v & 0xFFFFFCFCu) ? 0u : m;
 }
 
 // group index tables --------------------------------------------------------------------------------
@@ -134,34 +134,25 @@ struct Geo {
     uint32_t orient;                // loco
 };
 
+// Planes:  AGG / LOCO: p0 = particles, p1 = static not-enterable (boundary + padding)
+//          COAT:       p0 = particles, p1 = static not-enterable (boundary + padding + object), p2 = object
+//          SEP:        p0, p1 = colour bits, p2 = static not-enterable (boundary + padding)
 struct Lat {
     uint32_t* p0; uint32_t* p1; uint32_t* p2;
     uint16_t* pos; uint16_t* thr; uint16_t* light;
-    const uint32_t* dirtab;
+    const uint32_t* dirtab;         // [0..5] mask words, [8..13] packed position deltas
 };
 
-// --- cheap half of a proposal: where does particle idx go in direction d, and may it? -----------
-// kind: 0 = blocked (nothing happens, 2 draws), 1 = move into empty, 2 = swap (sep only)
-template <int BEH, int RW>
-__device__ __forceinline__ void probe(const Lat& L, uint32_t idx, uint32_t d, uint32_t& s, uint32_t& t, uint32_t& kind) {
-    s = L.pos[idx];
-    t = (uint32_t)((int)s + dir_delta(d));
-    uint32_t tr = t & 0xff, tc = t >> 8;
-    if (BEH == SEP) {
-        uint32_t occ = Plane<RW>::bit(L.p0, tr, tc) | Plane<RW>::bit(L.p1, tr, tc);
-        uint32_t inv = Plane<RW>::bit(L.p2, tr, tc);
-        kind = occ ? 2u : (inv ? 0u : 1u);
-    } else {
-        kind = Plane<RW>::bit(L.p1, tr, tc) ^ 1u;
-    }
+// locomotion.rs:260-290 on unpadded coordinates; light[b] = x | y << 8.  Beam id or -1 when the cell is on no beam.
+__device__ __forceinline__ int loco_beam(uint32_t o, int a, int x, int y) {
+    if (o == 1) { int b = 2 * x - y; return (b >= 0 && b <= 2 * a) ? b : -1; }
+    if (o == 2) { int b = 2 * y - x; return (b >= 0 && b <= 2 * a) ? b : -1; }
+    int sxy = x + y; return (sxy >= a && sxy <= 3 * a) ? sxy - a : -1;
 }
-
-// locomotion.rs:260-290 on unpadded coordinates; light[b] = x | y << 8
-__device__ __forceinline__ int loco_beam(uint32_t o, int a, int x, int y) { return o == 1 ? 2 * x - y : o == 2 ? 2 * y - x : x + y - a; }
-__device__ __forceinline__ uint32_t loco_sense(const uint16_t* light, uint32_t o, int a, int x, int y) {
-    if (o == 1) { int b = 2 * x - y; if (b >= 0 && b <= 2 * a) return y >= (int)(light[b] >> 8); return 0; }
-    if (o == 2) { int b = 2 * y - x; if (b >= 0 && b <= 2 * a) return x >= (int)(light[b] & 0xff); return 0; }
-    int sxy = x + y; if (sxy >= a && sxy <= 3 * a) return x >= (int)(light[sxy - a] & 0xff); return 0;
+__device__ __forceinline__ uint32_t loco_sense(const uint16_t* light, uint32_t o, int b, int x, int y) {
+    if (b < 0) return 0;
+    const uint32_t f = light[b];
+    return o == 1 ? (y >= (int)(f >> 8)) : (x >= (int)(f & 0xff));
 }
 
 __device__ __forceinline__ uint32_t sep_colour(const Geo& g, uint32_t idx) {   // hand-out order, separation.rs:126-146
@@ -173,140 +164,216 @@ __device__ __forceinline__ uint32_t same_mask(uint32_t w0, uint32_t w1, uint32_t
     return ~((w0 ^ m0) | (w1 ^ m1)) & 0x1ffu;
 }
 
-// --- expensive half: acceptance threshold of a possible proposal -------------------------------------
-template <int BEH, int RW>
-__device__ __forceinline__ uint32_t threshold(const Lat& L, const Geo& g, uint32_t idx, uint32_t d,
-                                              uint32_t s, uint32_t t, uint32_t kind, bool& noop) {
-    uint32_t sr = s & 0xff, sc = s >> 8, tr = t & 0xff, tc = t >> 8;
-    uint32_t tab = L.dirtab[d];
-    uint32_t mMid = tab & 0x1ff, mBack = (tab >> 9) & 0x1ff, mFront = tab >> 18;
-    noop = false;
+// --- one speculative proposal ---------------------------------------------------------------------------
+struct Prop {
+    uint32_t idx, d, pd;            // particle, direction, probability draw (0..999): fixed for the step
+    uint32_t s, t;                  // packed padded source / target
+    uint32_t tab;                   // dir_word(d)
+    uint32_t S0, T0;                // 3x3 windows of plane p0 around s and t
+    uint32_t S1, T1;                // SEP: windows of plane p1.  COAT: object windows (static)
+    uint32_t aux;                   // LOCO: light_idx*48 | beam(s)+1 << 8 | beam(t)+1 << 16.  SEP: mover colour
+    uint32_t kind;                  // 0 blocked, 1 move into empty, 2 swap (SEP)
+    bool bstat;                     // target statically not enterable
+    bool poss, eff;                 // target enterable now; would change the state
+};
+
+// decision from the registers (windows, static flag, draws): no lattice access, one or two threshold loads
+template <int BEH>
+__device__ __forceinline__ void derive(const Lat& L, const Geo& g, Prop& p) {
+    const uint32_t mMid = p.tab & 0x1ff, mBack = (p.tab >> 9) & 0x1ff, mFront = p.tab >> 18;
     if (BEH == AGG || BEH == LOCO) {
-        uint32_t S = win9<RW>(L.p0, sr, sc), T = win9<RW>(L.p0, tr, tc);
-        uint32_t gi = (__popc(S & mBack) * 3 + __popc(S & mMid)) * 4 + __popc(T & mFront);
-        if (BEH == LOCO) {
-            uint32_t cur = loco_sense(L.light, g.orient, (int)g.a, (int)sr - 1, (int)sc - 1);
-            uint32_t fut = loco_sense(L.light, g.orient, (int)g.a, (int)tr - 1, (int)tc - 1);
-            uint32_t li = (cur == fut) ? 2u : cur;           // (0,1)->0 (1,0)->1 else 2; locomotion.rs:230-235
-            gi += li * 48u;
-        }
-        return L.thr[gi];
+        uint32_t gi = (__popc(p.S0 & mBack) * 3 + __popc(p.S0 & mMid)) * 4 + __popc(p.T0 & mFront);
+        if (BEH == LOCO) gi += p.aux & 0xffu;
+        const uint32_t thr = L.thr[gi];
+        p.poss = !p.bstat && !((p.T0 >> 4) & 1u);            // mod.rs:235-251
+        p.kind = p.poss ? 1u : 0u;
+        p.eff = p.poss && p.pd < thr;                        // mod.rs:284-285
     } else if (BEH == COAT) {
-        uint32_t Sp = win9<RW>(L.p0, sr, sc), Tp = win9<RW>(L.p0, tr, tc);
-        uint32_t So = win9<RW>(L.p2, sr, sc), To = win9<RW>(L.p2, tr, tc);
-        uint32_t b = coat_idx3(__popc(Sp & mBack), __popc(So & mBack));
-        uint32_t m = coat_idx2(__popc(Sp & mMid), __popc(So & mMid));
-        uint32_t f = coat_idx3(__popc(Tp & mFront), __popc(To & mFront));
-        return L.thr[(b * 6 + m) * 10 + f];
+        const uint32_t b = coat_idx3(__popc(p.S0 & mBack), __popc(p.S1 & mBack));
+        const uint32_t m = coat_idx2(__popc(p.S0 & mMid), __popc(p.S1 & mMid));
+        const uint32_t f = coat_idx3(__popc(p.T0 & mFront), __popc(p.T1 & mFront));
+        const uint32_t thr = L.thr[(b * 6 + m) * 10 + f];
+        p.poss = !p.bstat && !((p.T0 >> 4) & 1u);            // coating.rs:515-530 (object cells are in bstat)
+        p.kind = p.poss ? 1u : 0u;
+        p.eff = p.poss && p.pd < thr;
     } else {
-        uint32_t S0 = win9<RW>(L.p0, sr, sc), S1 = win9<RW>(L.p1, sr, sc);
-        uint32_t T0 = win9<RW>(L.p0, tr, tc), T1 = win9<RW>(L.p1, tr, tc);
-        uint32_t oS = S0 | S1, oT = T0 | T1;
-        uint32_t col = sep_colour(g, idx);
-        uint32_t sS = same_mask(S0, S1, col), sT = same_mask(T0, T1, col);
-        uint32_t b = sep_idx(__popc(oS & mBack), __popc(sS & mBack));
-        uint32_t m = sep_idx(__popc(oS & mMid), __popc(sS & mMid));
-        uint32_t f = sep_idx(__popc(oT & mFront), __popc(sT & mFront));
-        uint32_t th = L.thr[(b * 6 + m) * 10 + f];
-        if (kind == 2) {
-            // the partner (at t) evaluated for the flipped move t -> s (separation.rs:768-778):
-            // its BACK is our FRONT, its FRONT our BACK, "same colour" relative to ITS colour.
-            uint32_t col2 = ((T0 >> 4) & 1u) | (((T1 >> 4) & 1u) << 1);
-            uint32_t pS = same_mask(S0, S1, col2), pT = same_mask(T0, T1, col2);
-            uint32_t b2 = sep_idx(__popc(oT & mFront), __popc(pT & mFront));
-            uint32_t m2 = sep_idx(__popc(oS & mMid), __popc(pS & mMid));
-            uint32_t f2 = sep_idx(__popc(oS & mBack), __popc(pS & mBack));
-            uint32_t th2 = L.thr[(b2 * 6 + m2) * 10 + f2];
-            th = min(th, th2);                               // max gene == min probability (tables are non-increasing)
-            noop = (col2 == col);                            // drawn and accepted but nothing moves (separation.rs:287-288)
-        }
-        return th;
+        const uint32_t oS = p.S0 | p.S1, oT = p.T0 | p.T1;
+        const uint32_t col = p.aux;
+        const uint32_t sS = same_mask(p.S0, p.S1, col), sT = same_mask(p.T0, p.T1, col);
+        const uint32_t b = sep_idx(__popc(oS & mBack), __popc(sS & mBack));
+        const uint32_t m = sep_idx(__popc(oS & mMid), __popc(sS & mMid));
+        const uint32_t f = sep_idx(__popc(oT & mFront), __popc(sT & mFront));
+        uint32_t thr = L.thr[(b * 6 + m) * 10 + f];
+        // the partner (at t) evaluated for the flipped move t -> s (separation.rs:768-778): its BACK is our
+        // FRONT, its FRONT our BACK, "same colour" relative to ITS colour.  Computed unconditionally
+        // (garbage when t is empty, then unused).
+        const uint32_t col2 = ((p.T0 >> 4) & 1u) | (((p.T1 >> 4) & 1u) << 1);
+        const uint32_t pS = same_mask(p.S0, p.S1, col2), pT = same_mask(p.T0, p.T1, col2);
+        const uint32_t b2 = sep_idx(__popc(oT & mFront), __popc(pT & mFront));
+        const uint32_t m2 = sep_idx(__popc(oS & mMid), __popc(pS & mMid));
+        const uint32_t f2 = sep_idx(__popc(oS & mBack), __popc(pS & mBack));
+        const uint32_t thr2 = L.thr[(b2 * 6 + m2) * 10 + f2];
+        p.kind = p.bstat ? 0u : (col2 ? 2u : 1u);            // separation.rs:720-740
+        p.poss = p.kind != 0;
+        if (p.kind == 2) thr = min(thr, thr2);               // max gene == min probability (tables are non-increasing)
+        // a same-colour swap draws and is accepted but nothing moves (separation.rs:287-288)
+        p.eff = p.poss && p.pd < thr && !(p.kind == 2 && col2 == col);
     }
 }
 
-// --- commit of lane f's accepted proposal ----------------------------------------------------------
-// AGG / COAT / LOCO: lane f alone flips its two cells in both planes (fire-and-forget shared atomics) and
-// rewrites its position.  SEP: a swap needs the partner's index (the reference's
-// participants.iter().position scan, separation.rs:302), found by a warp-wide scan, so every lane takes
-// part with lane f's data broadcast.
+// full evaluation of a proposal against the current lattice: position, windows, static flag, decision
 template <int BEH, int RW>
-__device__ __forceinline__ void commit(const Lat& L, const Geo& g, uint32_t lane, uint32_t f,
-                                       uint32_t idx, uint32_t s, uint32_t t, uint32_t kind) {
+__device__ __forceinline__ void evaluate(const Lat& L, const Geo& g, Prop& p) {
+    p.s = L.pos[p.idx];
+    p.tab = L.dirtab[p.d];
+    p.t = (p.s + L.dirtab[8 + p.d]) & 0xffffu;
+    const uint32_t sr = p.s & 0xff, sc = p.s >> 8, tr = p.t & 0xff, tc = p.t >> 8;
+    p.S0 = win9<RW>(L.p0, sr, sc);
+    p.T0 = win9<RW>(L.p0, tr, tc);
+    p.S1 = p.T1 = 0;
+    p.aux = 0;
     if (BEH == SEP) {
-        const uint32_t idxf = __shfl_sync(0xffffffffu, idx, f);
-        const uint32_t sf = __shfl_sync(0xffffffffu, s, f);
-        const uint32_t tf = __shfl_sync(0xffffffffu, t, f);
-        const uint32_t kindf = __shfl_sync(0xffffffffu, kind, f);
-        const uint32_t col = sep_colour(g, idxf);
+        p.S1 = win9<RW>(L.p1, sr, sc);
+        p.T1 = win9<RW>(L.p1, tr, tc);
+        p.bstat = Plane<RW>::bit(L.p2, tr, tc);
+        p.aux = sep_colour(g, p.idx);
+    } else {
+        p.bstat = Plane<RW>::bit(L.p1, tr, tc);
+        if (BEH == COAT) {
+            p.S1 = win9<RW>(L.p2, sr, sc);
+            p.T1 = win9<RW>(L.p2, tr, tc);
+        }
+        if (BEH == LOCO) {                                   // locomotion.rs:230-235, 596-598
+            const int a = (int)g.a, sx = (int)sr - 1, sy = (int)sc - 1, tx = (int)tr - 1, ty = (int)tc - 1;
+            const int bs = loco_beam(g.orient, a, sx, sy), bt = loco_beam(g.orient, a, tx, ty);
+            const uint32_t cur = loco_sense(L.light, g.orient, bs, sx, sy);
+            const uint32_t fut = loco_sense(L.light, g.orient, bt, tx, ty);
+            const uint32_t li = (cur == fut) ? 2u : cur;     // (0,1)->0 (1,0)->1 else 2
+            p.aux = li * 48u | ((uint32_t)(bs + 1) << 8) | ((uint32_t)(bt + 1) << 16);
+        }
+    }
+    derive<BEH>(L, g, p);
+}
+
+// cheap "is the target enterable" for the verification-mode alignment walk
+template <int BEH, int RW>
+__device__ __forceinline__ bool probe_possible(const Lat& L, uint32_t idx, uint32_t d) {
+    const uint32_t s = L.pos[idx];
+    const uint32_t t = (s + L.dirtab[8 + d]) & 0xffffu;
+    const uint32_t tr = t & 0xff, tc = t >> 8;
+    if (BEH == SEP) return !Plane<RW>::bit(L.p2, tr, tc);
+    return !(Plane<RW>::bit(L.p1, tr, tc) | Plane<RW>::bit(L.p0, tr, tc));
+}
+
+// --- commit of lane f's accepted proposal + incremental repair of every later lane --------------------
+// Lane f flips its two cells (fire-and-forget shared atomics) and rewrites its position.  Every lane then
+// patches its register windows with the flipped cells and re-derives; lanes that proposed the moved
+// particle itself (or, LOCO, that sense a rewritten beam) re-read the lattice.
+template <int BEH, int RW>
+__device__ __forceinline__ void commit_and_repair(const Lat& L, const Geo& g, uint32_t lane, uint32_t f, Prop& p) {
+    const uint32_t sf = __shfl_sync(0xffffffffu, p.s, f);
+    const uint32_t tf = __shfl_sync(0xffffffffu, p.t, f);
+    uint32_t x = 1;                                          // plane bits flipped at both cells
+    uint32_t wrote = 0;                                      // LOCO: rewritten beams (+1), 0 = none
+    if (BEH == SEP) {
+        // colour bits to flip: a move carries the mover's colour, a swap exchanges two colours
+        const uint32_t colf = __shfl_sync(0xffffffffu, p.aux, f);
+        const uint32_t kindf = __shfl_sync(0xffffffffu, p.kind, f);
+        const uint32_t idxf = __shfl_sync(0xffffffffu, p.idx, f);
+        x = colf;
         uint32_t partner = 0xffffffffu;
-        uint32_t x = col;                                    // colour bits to flip at both cells
         if (kindf == 2) {
+            // the partner's index: the reference's participants.iter().position scan (separation.rs:302),
+            // here a warp-wide scan of the position list
             for (uint32_t base = 0; base < g.n; base += 32) {
-                uint32_t i = base + lane;
-                uint32_t hit = __ballot_sync(0xffffffffu, i < g.n && L.pos[i] == tf);
+                const uint32_t i = base + lane;
+                const uint32_t hit = __ballot_sync(0xffffffffu, i < g.n && L.pos[i] == tf);
                 if (hit) { partner = base + __ffs(hit) - 1; break; }
             }
-            x = col ^ sep_colour(g, partner);
+            x = colf ^ sep_colour(g, partner);
         }
         if (lane == f) {
             const uint32_t sr = sf & 0xff, sc = sf >> 8, tr = tf & 0xff, tc = tf >> 8;
-            if (x & 1) { Plane<RW>::flip(L.p0, sr, sc); Plane<RW>::flip(L.p0, tr, tc); }
-            if (x & 2) { Plane<RW>::flip(L.p1, sr, sc); Plane<RW>::flip(L.p1, tr, tc); }
+            if (x & 1) { Plane<RW>::atom_xor(L.p0, sr, sc); Plane<RW>::atom_xor(L.p0, tr, tc); }
+            if (x & 2) { Plane<RW>::atom_xor(L.p1, sr, sc); Plane<RW>::atom_xor(L.p1, tr, tc); }
             L.pos[idxf] = (uint16_t)tf;
             if (kindf == 2) L.pos[partner] = (uint16_t)sf;
         }
     } else {
         if (lane == f) {
-            const uint32_t sr = s & 0xff, sc = s >> 8, tr = t & 0xff, tc = t >> 8;
+            const uint32_t sr = sf & 0xff, sc = sf >> 8, tr = tf & 0xff, tc = tf >> 8;
             if (BEH == LOCO) {                               // locomotion.rs:344-519, net effect
-                int a = (int)g.a, sx = (int)sr - 1, sy = (int)sc - 1, tx = (int)tr - 1, ty = (int)tc - 1;
-                uint32_t cur = loco_sense(L.light, g.orient, a, sx, sy);
-                uint32_t fut = loco_sense(L.light, g.orient, a, tx, ty);
-                if (cur) L.light[loco_beam(g.orient, a, sx, sy)] = (uint16_t)(sx | (sy << 8));
-                if (fut) L.light[loco_beam(g.orient, a, tx, ty)] = (uint16_t)(tx | (ty << 8));
+                const int sx = (int)sr - 1, sy = (int)sc - 1, tx = (int)tr - 1, ty = (int)tc - 1;
+                const int bs = (int)((p.aux >> 8) & 0xff) - 1, bt = (int)((p.aux >> 16) & 0xff) - 1;
+                const uint32_t cur = loco_sense(L.light, g.orient, bs, sx, sy);
+                const uint32_t fut = loco_sense(L.light, g.orient, bt, tx, ty);
+                if (cur) { L.light[bs] = (uint16_t)(sx | (sy << 8)); wrote = (uint32_t)(bs + 1); }
+                if (fut) { L.light[bt] = (uint16_t)(tx | (ty << 8)); wrote |= (uint32_t)(bt + 1) << 8; }
             }
-            Plane<RW>::atom_xor(L.p0, sr, sc); Plane<RW>::atom_xor(L.p0, tr, tc);
-            Plane<RW>::atom_xor(L.p1, sr, sc); Plane<RW>::atom_xor(L.p1, tr, tc);
-            L.pos[idx] = (uint16_t)t;
+            Plane<RW>::atom_xor(L.p0, sr, sc);
+            Plane<RW>::atom_xor(L.p0, tr, tc);
+            L.pos[p.idx] = (uint16_t)tf;
         }
+        if (BEH == LOCO) wrote = __shfl_sync(0xffffffffu, wrote, f);
     }
     __syncwarp();
+    // ---- repair (every lane; lanes <= f are finished and masked by the caller) ----
+    const uint32_t os = p.s - 0x0101u, ot = p.t - 0x0101u;
+    const uint32_t dS = win_bit(sf, os) ^ win_bit(tf, os);
+    const uint32_t dT = win_bit(sf, ot) ^ win_bit(tf, ot);
+    bool reread = (p.s == sf);                               // the moved particle itself was proposed again
+    if (BEH == SEP) {
+        if (x & 1) { p.S0 ^= dS; p.T0 ^= dT; }
+        if (x & 2) { p.S1 ^= dS; p.T1 ^= dT; }
+        reread |= (p.s == tf);                               // the swap partner was proposed
+    } else {
+        p.S0 ^= dS; p.T0 ^= dT;
+        if (BEH == LOCO && wrote) {
+            const uint32_t b1 = wrote & 0xff, b2 = wrote >> 8;
+            const uint32_t bs = (p.aux >> 8) & 0xff, bt = (p.aux >> 16) & 0xff;
+            reread |= (b1 && (bs == b1 || bt == b1)) || (b2 && (bs == b2 || bt == b2));
+        }
+    }
+    if (lane > f) {
+        if (reread) evaluate<BEH, RW>(L, g, p);
+        else derive<BEH>(L, g, p);
+    }
 }
 
-// --- conflict test between a lane's evaluation and a committed move -----------------------------------
-// A lane's read set is the cells adjacent-or-equal to its s or t; a commit writes sf and tf.  With
-// m = s + t (the doubled midpoint, per 8-bit field) any true conflict has |m - mf| <= 4 in both fields
-// (2|x - y| + |delta| + |delta_f| with |x - y| <= 1), so the box test below is a cheap superset; a false
-// positive only costs a re-evaluation.  Fields are spread to 16 bits so the biased subtraction cannot
-// borrow across them when in range.
-__device__ __forceinline__ uint32_t spread16(uint32_t m) { return __byte_perm(m, 0, 0x4140); }
-__device__ __forceinline__ bool box_conflict(uint32_t m32, uint32_t mf32) {
-    uint32_t x = m32 + 0x00040004u - mf32;
-    uint32_t y = x | (x + 0x00070007u);
-    return (y & 0xfff0fff0u) == 0u;
-}
-template <int BEH>
-__device__ __forceinline__ bool conflicts(const Geo& g, uint32_t s, uint32_t t, uint32_t m32, uint32_t sf, uint32_t tf, uint32_t mf32) {
-    bool cf = box_conflict(m32, mf32);
-    if (BEH == LOCO) {                                       // the light table is part of the read set
-        int a = (int)g.a;
-        int b1 = loco_beam(g.orient, a, (int)(sf & 0xff) - 1, (int)(sf >> 8) - 1);
-        int b2 = loco_beam(g.orient, a, (int)(tf & 0xff) - 1, (int)(tf >> 8) - 1);
-        int bs = loco_beam(g.orient, a, (int)(s & 0xff) - 1, (int)(s >> 8) - 1);
-        int bt = loco_beam(g.orient, a, (int)(t & 0xff) - 1, (int)(t >> 8) - 1);
-        cf |= (bs == b1) | (bs == b2) | (bt == b1) | (bt == b2);
+// --- commit rounds of one speculative batch ---------------------------------------------------------------
+// On entry every active lane holds a proposal evaluated against the current lattice; lane order = chain
+// order.  VERIFY: a repair that flips a lane's possible-ness changes how many draws that step consumes, so
+// the batch is cut at that lane (returned bound R; lanes >= R are not retired).
+template <int BEH, int RW, bool VERIFY>
+__device__ __forceinline__ uint32_t resolve_batch(const Lat& L, const Geo& g, uint32_t lane, bool active, Prop& p, uint32_t& ncommit) {
+    uint32_t R = 32;
+    for (;;) {
+        uint32_t A = __ballot_sync(0xffffffffu, p.eff);
+        if (VERIFY) A &= lowmask(R);
+        if (!A) break;
+        const uint32_t f = __ffs(A) - 1;
+        const bool was = p.poss;
+        commit_and_repair<BEH, RW>(L, g, lane, f, p);
+        if (lane <= f || !active) p.eff = false;
+        if (lane == f) ++ncommit;
+        if (VERIFY) {
+            const uint32_t X = __ballot_sync(0xffffffffu, active && lane > f && p.poss != was) & lowmask(R);
+            if (X) R = (uint32_t)__ffs(X) - 1;
+        }
     }
-    return cf;
+    return R;
 }
 
 // --- initial configuration ---------------------------------------------------------------------------
 template <int BEH, int RW>
 __device__ __forceinline__ uint32_t init_instance(const KParams& P, const Lat& L, const Geo& g, const Instance& in, uint32_t lane) {
     const uint32_t G = g.G, a = g.a, PG = G + 2;
-    uint32_t* blocked = (BEH == SEP) ? L.p2 : L.p1;
-    for (uint32_t w = lane; w < P.plane_words; w += 32) {
-        L.p0[w] = 0; L.p1[w] = 0;
-        if (BEH == SEP || BEH == COAT) L.p2[w] = 0;
+    uint32_t* pstat = (BEH == SEP) ? L.p2 : L.p1;
+    // zero every plane including its two guard rows
+    const int guarded = (int)P.plane_words + 2 * RW;
+    for (int w = (int)lane; w < guarded; w += 32) {
+        L.p0[w - RW] = 0; L.p1[w - RW] = 0;
+        if (BEH == SEP || BEH == COAT) L.p2[w - RW] = 0;
     }
     __syncwarp();
     // static "not enterable" mask: everything except arena cells |i - j| <= a (mod.rs:115-122)
@@ -325,7 +392,7 @@ __device__ __forceinline__ uint32_t init_instance(const KParams& P, const Lat& L
                     m = ~v;
                 }
             }
-            blocked[r * RW + w] = m;
+            pstat[r * RW + w] = m;
         }
     }
     __syncwarp();
@@ -367,9 +434,8 @@ __device__ __forceinline__ uint32_t init_instance(const KParams& P, const Lat& L
             uint32_t a01 = __shfl_sync(0xffffffffu, c01, src), a23 = __shfl_sync(0xffffffffu, c23, src);
             uint32_t cell = (((slot & 2) ? a23 : a01) >> ((slot & 1) * 16)) & 0xffffu;
             uint32_t pr = cell & 0xff, pc = cell >> 8;
-            bool free_ = true;
-            if (BEH == SEP) free_ = !(Plane<RW>::bit(L.p0, pr, pc) | Plane<RW>::bit(L.p1, pr, pc) | Plane<RW>::bit(L.p2, pr, pc));
-            else free_ = !Plane<RW>::bit(L.p1, pr, pc);
+            bool free_ = !(Plane<RW>::bit(L.p0, pr, pc) | Plane<RW>::bit(L.p1, pr, pc));
+            if (BEH == SEP) free_ = free_ && !Plane<RW>::bit(L.p2, pr, pc);
             uint32_t same = __match_any_sync(0xffffffffu, cell);
             bool acc = free_ && (lane == (uint32_t)(__ffs(same) - 1));
             uint32_t am = __ballot_sync(0xffffffffu, acc);
@@ -382,7 +448,6 @@ __device__ __forceinline__ uint32_t init_instance(const KParams& P, const Lat& L
                     if (col & 2) Plane<RW>::atom_or(L.p1, pr, pc);
                 } else {
                     Plane<RW>::atom_or(L.p0, pr, pc);
-                    Plane<RW>::atom_or(L.p1, pr, pc);
                 }
             }
             placed += __popc(am);
@@ -462,80 +527,6 @@ __device__ __forceinline__ void fitness(const KParams& P, const Lat& L, const Ge
     i1 = __reduce_add_sync(0xffffffffu, s1);
 }
 
-// --- evaluation of one proposal against the current lattice -------------------------------------------
-struct Prop {
-    uint32_t idx, d, pd;            // particle, direction, probability draw (0..999): fixed for the step
-    uint32_t s, t, kind, m32;       // evaluated: source, target, 0 blocked / 1 move / 2 swap, spread midpoint
-    bool poss, eff;                 // target enterable; would change the state
-};
-template <int BEH, int RW>
-__device__ __forceinline__ void evaluate(const Lat& L, const Geo& g, Prop& p) {
-    probe<BEH, RW>(L, p.idx, p.d, p.s, p.t, p.kind);
-    p.poss = p.kind != 0;
-    p.eff = false;
-    if (p.poss) {
-        bool noop;
-        uint32_t thr = threshold<BEH, RW>(L, g, p.idx, p.d, p.s, p.t, p.kind, noop);
-        p.eff = (p.pd < thr) && !noop;
-    }
-    p.m32 = spread16(p.s + p.t);
-}
-
-// --- commit / repair rounds of one speculative batch ---------------------------------------------------
-// On entry every active lane holds a proposal evaluated against the current lattice; lane order = chain
-// order.  Each round: (1) every lane tests itself against every pending accepted lane before it (the
-// "dirty" matrix, one shuffle per accepted lane); (2) all accepted lanes in front of the first dirty lane
-// commit at once — none of their read sets was touched, and their moves are pairwise far apart;
-// (3) lanes dirtied by a committed move re-evaluate with their own (fixed) random numbers.  The retired
-// sequence is exactly the sequential chain.  VERIFY: a re-evaluation that flips a lane's possible-ness
-// changes how many draws that step consumes, so the batch is cut at that lane (returned bound R).
-template <int BEH, int RW, bool VERIFY>
-__device__ __forceinline__ uint32_t resolve_batch(const Lat& L, const Geo& g, uint32_t lane, bool active, Prop& p, uint32_t& ncommit) {
-    uint32_t R = 32;
-    for (;;) {
-        uint32_t A = __ballot_sync(0xffffffffu, p.eff);
-        if (VERIFY) A &= lowmask(R);
-        if (!A) break;
-        uint32_t dirtyBy = 0, Ai = A;
-        do {
-            const uint32_t e = __ffs(Ai) - 1;
-            Ai &= Ai - 1;
-            const uint32_t mf32 = __shfl_sync(0xffffffffu, p.m32, e);
-            uint32_t sf = 0, tf = 0;
-            if (BEH == LOCO) { sf = __shfl_sync(0xffffffffu, p.s, e); tf = __shfl_sync(0xffffffffu, p.t, e); }
-            if (lane > e && conflicts<BEH>(g, p.s, p.t, p.m32, sf, tf, mf32)) dirtyBy |= 1u << e;
-        } while (Ai);
-        uint32_t D = __ballot_sync(0xffffffffu, active && dirtyBy != 0);
-        if (VERIFY) D &= lowmask(R);
-        const uint32_t bnd = D ? (uint32_t)__ffs(D) - 1 : 32u;
-        const uint32_t C = A & lowmask(bnd);                 // never empty: the first accepted lane cannot be dirty
-        if (BEH == SEP) {
-            uint32_t Ci = C;
-            do {
-                const uint32_t e = __ffs(Ci) - 1;
-                Ci &= Ci - 1;
-                commit<BEH, RW>(L, g, lane, e, p.idx, p.s, p.t, p.kind);
-            } while (Ci);
-        } else {
-            commit<BEH, RW>(L, g, lane, ((C >> lane) & 1u) ? lane : 32u, p.idx, p.s, p.t, p.kind);
-        }
-        if ((C >> lane) & 1u) { p.eff = false; ++ncommit; }
-        if (!D) break;                                       // nothing dirtied: every accepted lane has committed
-        const bool need = active && lane >= bnd && (dirtyBy & C) != 0 && (!VERIFY || lane < R);
-        bool changed = false;
-        if (need) {
-            const bool was = p.poss;
-            evaluate<BEH, RW>(L, g, p);
-            if (VERIFY && p.poss != was) { changed = true; p.eff = false; }
-        }
-        if (VERIFY) {
-            const uint32_t X = __ballot_sync(0xffffffffu, changed);
-            if (X) R = min(R, (uint32_t)__ffs(X) - 1);
-        }
-    }
-    return R;
-}
-
 // --- one instance, start to finish ------------------------------------------------------------------
 template <int BEH, int RW, int MODE>
 __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, const Instance& in, uint32_t lane) {
@@ -579,14 +570,14 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
         }
         if (tail) {
             const bool active = lane < tail;
-            cur.s = cur.t = cur.kind = cur.m32 = 0; cur.poss = cur.eff = false;
-            if (active) evaluate<BEH, RW>(L, g, cur);
+            evaluate<BEH, RW>(L, g, cur);
+            if (!active) { cur.eff = false; cur.poss = false; }
             resolve_batch<BEH, RW, false>(L, g, lane, active, cur, ncommit);
             nposs += (active && cur.poss) ? 1u : 0u;
         }
     } else {
         // Verification mode: the number of draws a step consumes (2 if blocked, 3 if possible) decides
-        // where the next step starts in the WyRand chain, so lanes evaluate both alignments and a
+        // where the next step starts in the WyRand chain, so lanes probe both alignments and a
         // warp-uniform walk over the "possible" ballots picks the real ones.  A commit that flips a later
         // lane's possible-ness invalidates that alignment: the batch is cut there.
         uint64_t k = 0, cbase = 0;                           // steps retired, thread-local draws consumed
@@ -600,10 +591,8 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
             // a step starting in the even slot uses (rE, rO, next rE); in the odd slot (rO, next rE, next rO)
             const uint32_t idxE = wy_mod_u64(rE, n, ms, kE), dE = wy_mod_u64(rO, 6, ms, kO);
             const uint32_t idxO = wy_mod_u64(rO, n, ms, kO), dO = wy_mod_u64(nE, 6, ms, kO + 1);
-            uint32_t sE, tE, kindE, sO, tO, kindO;
-            probe<BEH, RW>(L, idxE, dE, sE, tE, kindE);
-            probe<BEH, RW>(L, idxO, dO, sO, tO, kindO);
-            const uint32_t PE = __ballot_sync(0xffffffffu, kindE != 0), PO = __ballot_sync(0xffffffffu, kindO != 0);
+            const uint32_t PE = __ballot_sync(0xffffffffu, probe_possible<BEH, RW>(L, idxE, dE));
+            const uint32_t PO = __ballot_sync(0xffffffffu, probe_possible<BEH, RW>(L, idxO, dO));
             // which slots start a real step: a blocked step consumes 2 draws, a possible one 3
             uint32_t realE = 0, realO = 0, l = 0, par = 0;
             while (l < 31) {
@@ -620,20 +609,13 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
             const bool active = (myE || myO) && (uint64_t)ord < rem;
             Prop p;
             p.idx = myO ? idxO : idxE; p.d = myO ? dO : dE;
-            p.s = myO ? sO : sE; p.t = myO ? tO : tE; p.kind = active ? (myO ? kindO : kindE) : 0u;
-            p.poss = p.kind != 0;
-            p.eff = false;
-            p.pd = 0;
-            if (p.poss) {
-                bool noop;
-                uint32_t thr = threshold<BEH, RW>(L, g, p.idx, p.d, p.s, p.t, p.kind, noop);
-                p.pd = wy_mod_1000(myO ? nO32 : (uint32_t)nE, ms, (myO ? kO : kE) + 2);
-                p.eff = (p.pd < thr) && !noop;
-            }
-            p.m32 = spread16(p.s + p.t);
+            // the probability draw exists only for a possible step; computing it for every lane is harmless
+            p.pd = wy_mod_1000(myO ? nO32 : (uint32_t)nE, ms, (myO ? kO : kE) + 2);
+            evaluate<BEH, RW>(L, g, p);
+            if (!active) { p.eff = false; p.poss = false; }
             const uint32_t am = __ballot_sync(0xffffffffu, active);
             const uint32_t R = resolve_batch<BEH, RW, true>(L, g, lane, active, p, ncommit);
-            nposs += (p.poss && lane < R) ? 1u : 0u;
+            nposs += (active && p.poss && lane < R) ? 1u : 0u;
             k += __popc(am & lowmask(R));
             if (R < 32) cbase += 2 * R + __shfl_sync(0xffffffffu, (uint32_t)myO, R);   // the cut lane restarts the next batch
             else cbase += q_end;
@@ -677,8 +659,11 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
 template <int BEH, int RW, int MODE>
 __global__ void __launch_bounds__(256) sops_chain_kernel(const KParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
-    __shared__ uint32_t s_dirtab[8];
-    if (threadIdx.x < 6) s_dirtab[threadIdx.x] = dir_word((int)threadIdx.x);
+    __shared__ uint32_t s_dirtab[16];
+    if (threadIdx.x < 6) {
+        s_dirtab[threadIdx.x] = dir_word((int)threadIdx.x);
+        s_dirtab[8 + threadIdx.x] = (uint32_t)dir_delta((int)threadIdx.x);
+    }
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* base = smem + (size_t)warp * P.words_per_warp;
