@@ -206,13 +206,10 @@ void layout_group(Group& g, int beh, uint32_t max_pg, uint32_t max_n) {
     g.plane_words = ((max_pg * (uint32_t)g.rw) + 1u) & ~1u;     // keep 64-bit rows 8-byte aligned
     g.pos_words = ((max_n + 1) / 2 + 1u) & ~1u;
     uint32_t thr_words = (uint32_t)genome_len(beh) / 2;
-    // every plane carries one guard row above row 0 and one below the last row (3x3 windows of cells in
-    // the padding ring read them); off_p* point at row 0
-    const uint32_t guard = (uint32_t)g.rw, span = g.plane_words + 2 * guard;
     uint32_t off = 0;
-    g.off_p0 = off + guard; off += span;
-    g.off_p1 = off + guard; off += span;
-    g.off_p2 = off + guard; if (three) off += span;
+    g.off_p0 = off; off += g.plane_words;
+    g.off_p1 = off; off += g.plane_words;
+    g.off_p2 = off; if (three) off += g.plane_words;
     g.off_pos = off; off += g.pos_words;
     g.off_thr = off; off += thr_words;
     g.off_aux = off; if (beh == SOPS_LOCO) off += SOPS_LIGHT_WORDS;
@@ -319,9 +316,8 @@ int sops_batch_prepare(sops_ctx* ctx, int behavior, const uint8_t* genomes, uint
     for (uint32_t t = 0; t < T; ++t) {
         int rc = shape_of(behavior, trial_sizes[t], &shp[t]);
         if (rc) return fail(ctx, rc, "invalid size tuple at trial " + std::to_string(t));
-        if (shp[t].G + 2 > 64) return fail(ctx, SOPS_E_UNSUPPORTED, "arena_layers > 30 not implemented by the kernels");
-        if (behavior == SOPS_LOCO && trial_sizes[t].arena > 30) return fail(ctx, SOPS_E_UNSUPPORTED, "loco arena_layers > 30");
-    }
+        if (shp[t].G + 4 > 64) return fail(ctx, SOPS_E_UNSUPPORTED, "arena_layers > 29 not implemented by the kernels");
+            }
     if (loco_orient && behavior == SOPS_LOCO)
         for (uint32_t q = 0; q < N; ++q)
             if (loco_orient[q] < 1 || loco_orient[q] > 3) return fail(ctx, SOPS_E_ARG, "loco orientation must be 1..3");
@@ -405,7 +401,7 @@ int sops_batch_prepare(sops_ctx* ctx, int behavior, const uint8_t* genomes, uint
         if (d.n_inst == 0) continue;
         // split by row-width class (stable: keeps the cost order inside each class)
         std::vector<uint32_t> cls[2];
-        for (uint32_t q : d.global_of) cls[(shp[q % T].G + 2 > 32) ? 1 : 0].push_back(q);
+        for (uint32_t q : d.global_of) cls[(shp[q % T].G + 4 > 32) ? 1 : 0].push_back(q);
         d.global_of.clear();
         CK(grow_host(&d.h_inst, &d.hcap_inst, (size_t)d.n_inst));
         size_t dump_words = 0;
@@ -419,7 +415,7 @@ int sops_batch_prepare(sops_ctx* ctx, int behavior, const uint8_t* genomes, uint
             uint32_t max_pg = 0, max_n = 0;
             for (uint32_t q : cls[c]) {
                 uint32_t t = q % T;
-                max_pg = std::max(max_pg, shp[t].G + 2);
+                max_pg = std::max(max_pg, shp[t].G + 4);
                 max_n = std::max(max_n, shp[t].n);
                 Instance in;
                 memset(&in, 0, sizeof(in));
@@ -661,9 +657,9 @@ int sops_dump_state(sops_ctx* ctx, uint32_t instance, uint8_t* grid, uint8_t* pa
                 uint8_t v;
                 const bool bnd = (i - j > a) || (j - i > a);
                 switch (ctx->behavior) {
-                case SOPS_SEP: v = bnd ? 4 : (uint8_t)(bit(0, i + 1, j + 1) | (bit(1, i + 1, j + 1) << 1)); break;
-                case SOPS_COAT: v = bnd ? 7 : bit(2, i + 1, j + 1) ? 2 : (uint8_t)bit(0, i + 1, j + 1); break;
-                default: v = bnd ? 2 : (uint8_t)bit(0, i + 1, j + 1); break;
+                case SOPS_SEP: v = bnd ? 4 : (uint8_t)(bit(0, i + 2, j + 2) | (bit(1, i + 2, j + 2) << 1)); break;
+                case SOPS_COAT: v = bnd ? 7 : bit(2, i + 2, j + 2) ? 2 : (uint8_t)bit(0, i + 2, j + 2); break;
+                default: v = bnd ? 2 : (uint8_t)bit(0, i + 2, j + 2); break;
                 }
                 grid[(size_t)i * G + j] = v;
             }
@@ -672,8 +668,8 @@ int sops_dump_state(sops_ctx* ctx, uint32_t instance, uint8_t* grid, uint8_t* pa
         const uint16_t* pos = reinterpret_cast<const uint16_t*>(src + 3 * pw);
         const uint32_t n3 = sh.n / 3;
         for (uint32_t k = 0; k < sh.n; ++k) {
-            particles[3 * k] = (uint8_t)((pos[k] & 0xff) - 1);
-            particles[3 * k + 1] = (uint8_t)((pos[k] >> 8) - 1);
+            particles[3 * k] = (uint8_t)((pos[k] & 0xff) - 2);
+            particles[3 * k + 1] = (uint8_t)((pos[k] >> 8) - 2);
             particles[3 * k + 2] = ctx->behavior == SOPS_SEP ? (uint8_t)(1 + (k >= n3) + (k >= 2 * n3)) : 0;
         }
     }

@@ -11,9 +11,10 @@
 //     particle list as packed u16 (row+1 | (col+1) << 8), the genome as u16 acceptance thresholds.
 //   * The Markov chain is strictly sequential, but only ~0.3-15 % of proposals change the state.  The 32
 //     lanes therefore evaluate the next 32 proposals SPECULATIVELY against the current lattice and keep
-//     what they read — the two 3x3 bit windows around source and target — in registers.  The lowest
-//     accepted lane commits; every later lane patches its windows with the two flipped cells (pure
-//     register arithmetic, exact) and re-derives its decision; then the next accepted lane commits.
+//     what they read — the 5x5 bit window around the source, which contains every cell adjacent to source
+//     or target — in a register.  The lowest accepted lane commits; every later lane patches its window
+//     with the two flipped cells (register arithmetic, exact) and re-derives its decision only if a bit
+//     really changed; then the next accepted lane commits.
 //     All 32 steps retire every batch and the retired sequence is exactly the sequential chain.
 //   * Both RNG modes are counter based: fast = Philox2x32-10 keyed per step; verify = the WyRand
 //     double chain, whose draw count per step (2 or 3) depends on the state — resolved per batch by a
@@ -54,11 +55,11 @@ struct KParams {
     uint32_t dump_stride;
     uint32_t dump_slot0;            // first slot of this launch (dump rows are launch-relative)
     const uint16_t* coat_dist;      // coat: per-size G*G distance tables (0xFFFF = none)
-    // per-warp shared-memory layout, in 32-bit words.  Each plane has one guard row above row 0 and one
-    // below row PG-1 (windows of cells in the padding ring read them); off_p* point at row 0.
+    // per-warp shared-memory layout, in 32-bit words.  The grid is padded by TWO cells on every side
+    // (PG = G + 4) so the 5x5 window of any particle stays inside the plane.
     uint32_t words_per_warp;
     uint32_t off_p0, off_p1, off_p2, off_pos, off_thr, off_aux;
-    uint32_t plane_words, pos_words;    // plane_words: rows 0..PG-1 as dumped (without the guard rows)
+    uint32_t plane_words, pos_words;
 };
 
 #define SOPS_LIGHT_WORDS 32u        // 64 u16 beams (a <= 30 -> 2a+1 <= 61)
@@ -82,43 +83,81 @@ __host__ __device__ constexpr uint32_t dir_word(int d) {
            ((NB_MASK & ~dir_mid(d ^ 1) & ~(1u << dir_bit(d ^ 1))) << 18);
 }
 // packed position delta of direction d on (row | col << 8):  -1, +1, -256, +256, -257, +257
-__host__ __device__ constexpr int dir_delta(int d) {
-    return d == 0 ? -1 : d == 1 ? 1 : d == 2 ? -256 : d == 3 ? 256 : d == 4 ? -257 : 257;
+__host__ __device__ constexpr int dir_dr(int d) { return d == 0 || d == 4 ? -1 : d == 1 || d == 5 ? 1 : 0; }
+__host__ __device__ constexpr int dir_dc(int d) { return d == 2 || d == 4 ? -1 : d == 3 || d == 5 ? 1 : 0; }
+__host__ __device__ constexpr int dir_delta(int d) { return dir_dr(d) + 256 * dir_dc(d); }
+// The 5x5 window U around the source s (bit = 5*(dr+2) + (dc+2), s at bit 12) contains both 3x3 windows:
+// 3x3 bit (r, c) of the window centred at s + (or, oc) sits at U bit 5*(r+1+or) + (c+1+oc).
+__host__ __device__ constexpr uint32_t lift9(uint32_t m9, int orow, int ocol) {
+    uint32_t m = 0;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c)
+            if ((m9 >> (3 * r + c)) & 1u) m |= 1u << (5 * (r + 1 + orow) + (c + 1 + ocol));
+    return m;
 }
+__host__ __device__ constexpr uint32_t dir_back5(int d) { return lift9((dir_word(d) >> 9) & 0x1ff, 0, 0); }
+__host__ __device__ constexpr uint32_t dir_mid5(int d) { return lift9(dir_word(d) & 0x1ff, 0, 0); }
+__host__ __device__ constexpr uint32_t dir_front5(int d) { return lift9(dir_word(d) >> 18, dir_dr(d), dir_dc(d)); }
+__host__ __device__ constexpr uint32_t dir_tbit(int d) { return (uint32_t)(12 + 5 * dir_dr(d) + dir_dc(d)); }
+// 4-bit direction code (dr+1) | (dc+1) << 2, so that delta = (code & 3) + ((code >> 2) << 8) - 0x0101
+__host__ __device__ constexpr uint32_t dir_code(int d) { return (uint32_t)((dir_dr(d) + 1) | ((dir_dc(d) + 1) << 2)); }
 
 __device__ __forceinline__ uint32_t lowmask(uint32_t r) { return r >= 32 ? 0xffffffffu : ((1u << r) - 1u); }
+
+// Predicated shared-memory updates: operands are computed by every lane (they are warp-uniform in the
+// commit path, so the work overlaps the repair arithmetic), only lanes with q set issue the access.
+__device__ __forceinline__ void pred_xor_shared(bool q, const uint32_t* addr, uint32_t mask) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q red.shared.xor.b32 [%1], %2;\n\t}"
+                 :: "r"((uint32_t)q), "r"((uint32_t)__cvta_generic_to_shared(addr)), "r"(mask) : "memory");
+}
+__device__ __forceinline__ void pred_store_u16(bool q, const uint16_t* addr, uint32_t v) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.shared.u16 [%1], %2;\n\t}"
+                 :: "r"((uint32_t)q), "r"((uint32_t)__cvta_generic_to_shared(addr)), "h"((uint16_t)v) : "memory");
+}
 
 // ------------------------------------------------------------------------------ bit planes ------
 template <int RW> struct Plane;
 template <> struct Plane<1> {       // padded grid side <= 32: one u32 per row
-    static __device__ __forceinline__ uint32_t win(const uint32_t* p, int r, uint32_t cm1) { return (p[r] >> (cm1 & 31u)) & 7u; }
+    static __device__ __forceinline__ uint32_t seg(const uint32_t* p, uint32_t r, uint32_t c0, uint32_t m) { return (p[r] >> c0) & m; }
     static __device__ __forceinline__ uint32_t bit(const uint32_t* p, uint32_t r, uint32_t c) { return (p[r] >> c) & 1u; }
     static __device__ __forceinline__ void atom_or(uint32_t* p, uint32_t r, uint32_t c) { atomicOr(&p[r], 1u << c); }
     static __device__ __forceinline__ void atom_xor(uint32_t* p, uint32_t r, uint32_t c) { atomicXor(&p[r], 1u << c); }
+    static __device__ __forceinline__ const uint32_t* word(const uint32_t* p, uint32_t r, uint32_t c) { return p + r; }
 };
 template <> struct Plane<2> {       // padded grid side <= 64: one u64 per row
-    static __device__ __forceinline__ uint32_t win(const uint32_t* p, int r, uint32_t cm1) {
+    static __device__ __forceinline__ uint32_t seg(const uint32_t* p, uint32_t r, uint32_t c0, uint32_t m) {
         uint64_t w = *reinterpret_cast<const uint64_t*>(p + 2 * r);
-        return (uint32_t)(w >> (cm1 & 63u)) & 7u;
+        return (uint32_t)(w >> c0) & m;
     }
     static __device__ __forceinline__ uint32_t bit(const uint32_t* p, uint32_t r, uint32_t c) { return (p[2 * r + (c >> 5)] >> (c & 31)) & 1u; }
     static __device__ __forceinline__ void atom_or(uint32_t* p, uint32_t r, uint32_t c) { atomicOr(&p[2 * r + (c >> 5)], 1u << (c & 31)); }
     static __device__ __forceinline__ void atom_xor(uint32_t* p, uint32_t r, uint32_t c) { atomicXor(&p[2 * r + (c >> 5)], 1u << (c & 31)); }
+    static __device__ __forceinline__ const uint32_t* word(const uint32_t* p, uint32_t r, uint32_t c) { return p + 2 * r + (c >> 5); }
 };
 
-// 3x3 window around padded cell (r, c); r-1 / r+1 may be a guard row, c-1 may be -1 (garbage bits that the
-// caller never uses: such a cell is statically blocked)
+// 3x3 window around padded cell (r, c): bit = 3*row + col (fitness sums)
 template <int RW>
 __device__ __forceinline__ uint32_t win9(const uint32_t* p, uint32_t r, uint32_t c) {
-    const int ri = (int)r;
-    return Plane<RW>::win(p, ri - 1, c - 1) | (Plane<RW>::win(p, ri, c - 1) << 3) | (Plane<RW>::win(p, ri + 1, c - 1) << 6);
+    return Plane<RW>::seg(p, r - 1, c - 1, 7u) | (Plane<RW>::seg(p, r, c - 1, 7u) << 3) | (Plane<RW>::seg(p, r + 1, c - 1, 7u) << 6);
 }
-
-// window bit of cell x (packed) in the 3x3 window whose top-left cell is `org` (= centre - 0x0101); 0 if outside
-__device__ __forceinline__ uint32_t win_bit(uint32_t x, uint32_t org) {
-    const uint32_t v = x - org;                              // (dr + 1) | (dc + 1) << 8 when inside
-    const uint32_t m = ((1u << ((v >> 8) & 31u)) & 7u) << ((v & 3u) * 3u);   // row 3 lands above bit 8: ignored by every mask
-    return (v & 0xFFFFFCFCu) ? 0u : m;
+// 5x5 window around padded cell (r, c): bit = 5*row + col.  r, c >= 2 always (two padding cells).
+template <int RW>
+__device__ __forceinline__ uint32_t win25(const uint32_t* p, uint32_t r, uint32_t c) {
+    const uint32_t c0 = c - 2;
+    return Plane<RW>::seg(p, r - 2, c0, 31u) | (Plane<RW>::seg(p, r - 1, c0, 31u) << 5) | (Plane<RW>::seg(p, r, c0, 31u) << 10) |
+           (Plane<RW>::seg(p, r + 1, c0, 31u) << 15) | (Plane<RW>::seg(p, r + 2, c0, 31u) << 20);
+}
+// XOR mask of the two flipped cells x and x + delta (a committed move) in the 5x5 window whose top-left
+// cell is `org` (= centre - 0x0202); kd = 5*dr + dc of the move.  Cells outside the window contribute 0.
+__device__ __forceinline__ uint32_t win25_patch(uint32_t x, uint32_t delta, int kd, uint32_t org) {
+    const uint32_t v = x - org;                              // (dr + 2) | (dc + 2) << 8 when inside
+    const uint32_t w = v + delta;
+    const bool vin = ((v | (v + 0x0303u)) & 0xFFFFF8F8u) == 0u;   // both fields in 0..4 (a borrow sets high bits)
+    const bool win_ = ((w | (w + 0x0303u)) & 0xFFFFF8F8u) == 0u;
+    (void)kd;
+    const uint32_t iv = (v & 7u) * 5u + (v >> 8), iw = (w & 7u) * 5u + (w >> 8);
+    const uint32_t mv = 1u << (iv & 31u), mw = 1u << (iw & 31u);
+    return (vin ? mv : 0u) ^ (win_ ? mw : 0u);
 }
 
 // group index tables --------------------------------------------------------------------------------
@@ -140,7 +179,7 @@ struct Geo {
 struct Lat {
     uint32_t* p0; uint32_t* p1; uint32_t* p2;
     uint16_t* pos; uint16_t* thr; uint16_t* light;
-    const uint32_t* dirtab;         // [0..5] mask words, [8..13] packed position deltas
+    const uint4* dirtab;            // per direction: back5, mid5, front5 masks, delta | tbit << 16 | code << 24
 };
 
 // locomotion.rs:260-290 on unpadded coordinates; light[b] = x | y << 8.  Beam id or -1 when the cell is on no beam.
@@ -168,88 +207,93 @@ __device__ __forceinline__ uint32_t same_mask(uint32_t w0, uint32_t w1, uint32_t
 struct Prop {
     uint32_t idx, d, pd;            // particle, direction, probability draw (0..999): fixed for the step
     uint32_t s, t;                  // packed padded source / target
-    uint32_t tab;                   // dir_word(d)
-    uint32_t S0, T0;                // 3x3 windows of plane p0 around s and t
-    uint32_t S1, T1;                // SEP: windows of plane p1.  COAT: object windows (static)
-    uint32_t aux;                   // LOCO: light_idx*48 | beam(s)+1 << 8 | beam(t)+1 << 16.  SEP: mover colour
+    uint32_t tt;                    // t | tbit << 16 | dir_code << 24 | SEP: flipped colour bits << 28 (what an accepted lane broadcasts)
+    uint32_t mB, mM, mF, tb;        // BACK / MID / FRONT masks in the 5x5 window, bit of the target cell | dir_code << 8
+    uint32_t U0;                    // 5x5 window of plane p0 around s
+    uint32_t U1;                    // SEP: 5x5 window of plane p1.  COAT: object window (static)
+    uint32_t aux;                   // LOCO: light_idx*48 | beam(s)+1 << 8 | beam(t)+1 << 16 | senses(s) << 24 | senses(t) << 25.  SEP: mover colour
     uint32_t kind;                  // 0 blocked, 1 move into empty, 2 swap (SEP)
     bool bstat;                     // target statically not enterable
     bool poss, eff;                 // target enterable now; would change the state
 };
 
-// decision from the registers (windows, static flag, draws): no lattice access, one or two threshold loads
+// 25-bit mask of window cells whose 2-bit colour equals col (col != 0 so empty cells never match)
+__device__ __forceinline__ uint32_t same_mask25(uint32_t w0, uint32_t w1, uint32_t col) {
+    uint32_t m0 = (col & 1) ? 0xffffffffu : 0u, m1 = (col & 2) ? 0xffffffffu : 0u;
+    return ~((w0 ^ m0) | (w1 ^ m1));
+}
+
+// decision from the registers (window, static flag, draws): no lattice access, one or two threshold loads
 template <int BEH>
 __device__ __forceinline__ void derive(const Lat& L, const Geo& g, Prop& p) {
-    const uint32_t mMid = p.tab & 0x1ff, mBack = (p.tab >> 9) & 0x1ff, mFront = p.tab >> 18;
     if (BEH == AGG || BEH == LOCO) {
-        uint32_t gi = (__popc(p.S0 & mBack) * 3 + __popc(p.S0 & mMid)) * 4 + __popc(p.T0 & mFront);
+        uint32_t gi = (__popc(p.U0 & p.mB) * 3 + __popc(p.U0 & p.mM)) * 4 + __popc(p.U0 & p.mF);
         if (BEH == LOCO) gi += p.aux & 0xffu;
         const uint32_t thr = L.thr[gi];
-        p.poss = !p.bstat && !((p.T0 >> 4) & 1u);            // mod.rs:235-251
+        p.poss = !p.bstat && !((p.U0 >> (p.tb & 31u)) & 1u);         // mod.rs:235-251
         p.kind = p.poss ? 1u : 0u;
         p.eff = p.poss && p.pd < thr;                        // mod.rs:284-285
     } else if (BEH == COAT) {
-        const uint32_t b = coat_idx3(__popc(p.S0 & mBack), __popc(p.S1 & mBack));
-        const uint32_t m = coat_idx2(__popc(p.S0 & mMid), __popc(p.S1 & mMid));
-        const uint32_t f = coat_idx3(__popc(p.T0 & mFront), __popc(p.T1 & mFront));
+        const uint32_t b = coat_idx3(__popc(p.U0 & p.mB), __popc(p.U1 & p.mB));
+        const uint32_t m = coat_idx2(__popc(p.U0 & p.mM), __popc(p.U1 & p.mM));
+        const uint32_t f = coat_idx3(__popc(p.U0 & p.mF), __popc(p.U1 & p.mF));
         const uint32_t thr = L.thr[(b * 6 + m) * 10 + f];
-        p.poss = !p.bstat && !((p.T0 >> 4) & 1u);            // coating.rs:515-530 (object cells are in bstat)
+        p.poss = !p.bstat && !((p.U0 >> (p.tb & 31u)) & 1u);         // coating.rs:515-530 (object cells are in bstat)
         p.kind = p.poss ? 1u : 0u;
         p.eff = p.poss && p.pd < thr;
     } else {
-        const uint32_t oS = p.S0 | p.S1, oT = p.T0 | p.T1;
+        const uint32_t occ = p.U0 | p.U1;
         const uint32_t col = p.aux;
-        const uint32_t sS = same_mask(p.S0, p.S1, col), sT = same_mask(p.T0, p.T1, col);
-        const uint32_t b = sep_idx(__popc(oS & mBack), __popc(sS & mBack));
-        const uint32_t m = sep_idx(__popc(oS & mMid), __popc(sS & mMid));
-        const uint32_t f = sep_idx(__popc(oT & mFront), __popc(sT & mFront));
+        const uint32_t sm = same_mask25(p.U0, p.U1, col);
+        const uint32_t oB = __popc(occ & p.mB), oM = __popc(occ & p.mM), oF = __popc(occ & p.mF);
+        const uint32_t b = sep_idx(oB, __popc(sm & p.mB));
+        const uint32_t m = sep_idx(oM, __popc(sm & p.mM));
+        const uint32_t f = sep_idx(oF, __popc(sm & p.mF));
         uint32_t thr = L.thr[(b * 6 + m) * 10 + f];
         // the partner (at t) evaluated for the flipped move t -> s (separation.rs:768-778): its BACK is our
         // FRONT, its FRONT our BACK, "same colour" relative to ITS colour.  Computed unconditionally
         // (garbage when t is empty, then unused).
-        const uint32_t col2 = ((p.T0 >> 4) & 1u) | (((p.T1 >> 4) & 1u) << 1);
-        const uint32_t pS = same_mask(p.S0, p.S1, col2), pT = same_mask(p.T0, p.T1, col2);
-        const uint32_t b2 = sep_idx(__popc(oT & mFront), __popc(pT & mFront));
-        const uint32_t m2 = sep_idx(__popc(oS & mMid), __popc(pS & mMid));
-        const uint32_t f2 = sep_idx(__popc(oS & mBack), __popc(pS & mBack));
+        const uint32_t col2 = ((p.U0 >> (p.tb & 31u)) & 1u) | (((p.U1 >> (p.tb & 31u)) & 1u) << 1);
+        const uint32_t pm = same_mask25(p.U0, p.U1, col2);
+        const uint32_t b2 = sep_idx(oF, __popc(pm & p.mF));
+        const uint32_t m2 = sep_idx(oM, __popc(pm & p.mM));
+        const uint32_t f2 = sep_idx(oB, __popc(pm & p.mB));
         const uint32_t thr2 = L.thr[(b2 * 6 + m2) * 10 + f2];
         p.kind = p.bstat ? 0u : (col2 ? 2u : 1u);            // separation.rs:720-740
         p.poss = p.kind != 0;
         if (p.kind == 2) thr = min(thr, thr2);               // max gene == min probability (tables are non-increasing)
         // a same-colour swap draws and is accepted but nothing moves (separation.rs:287-288)
         p.eff = p.poss && p.pd < thr && !(p.kind == 2 && col2 == col);
+        p.tt = (p.tt & 0x0fffffffu) | ((col ^ col2) << 28);     // a move flips col (col2 == 0), a swap col ^ col2
     }
 }
 
-// full evaluation of a proposal against the current lattice: position, windows, static flag, decision
+// full evaluation of a proposal against the current lattice: position, window, static flag, decision
 template <int BEH, int RW>
 __device__ __forceinline__ void evaluate(const Lat& L, const Geo& g, Prop& p) {
     p.s = L.pos[p.idx];
-    p.tab = L.dirtab[p.d];
-    p.t = (p.s + L.dirtab[8 + p.d]) & 0xffffu;
+    const uint4 dt = L.dirtab[p.d];
+    p.mB = dt.x; p.mM = dt.y; p.mF = dt.z; p.tb = dt.w >> 16;                // tbit | code << 8
+    p.t = (p.s + dt.w) & 0xffffu;
+    p.tt = p.t | (dt.w & 0xffff0000u);
     const uint32_t sr = p.s & 0xff, sc = p.s >> 8, tr = p.t & 0xff, tc = p.t >> 8;
-    p.S0 = win9<RW>(L.p0, sr, sc);
-    p.T0 = win9<RW>(L.p0, tr, tc);
-    p.S1 = p.T1 = 0;
+    p.U0 = win25<RW>(L.p0, sr, sc);
+    p.U1 = 0;
     p.aux = 0;
     if (BEH == SEP) {
-        p.S1 = win9<RW>(L.p1, sr, sc);
-        p.T1 = win9<RW>(L.p1, tr, tc);
+        p.U1 = win25<RW>(L.p1, sr, sc);
         p.bstat = Plane<RW>::bit(L.p2, tr, tc);
         p.aux = sep_colour(g, p.idx);
     } else {
         p.bstat = Plane<RW>::bit(L.p1, tr, tc);
-        if (BEH == COAT) {
-            p.S1 = win9<RW>(L.p2, sr, sc);
-            p.T1 = win9<RW>(L.p2, tr, tc);
-        }
+        if (BEH == COAT) p.U1 = win25<RW>(L.p2, sr, sc);
         if (BEH == LOCO) {                                   // locomotion.rs:230-235, 596-598
-            const int a = (int)g.a, sx = (int)sr - 1, sy = (int)sc - 1, tx = (int)tr - 1, ty = (int)tc - 1;
+            const int a = (int)g.a, sx = (int)sr - 2, sy = (int)sc - 2, tx = (int)tr - 2, ty = (int)tc - 2;
             const int bs = loco_beam(g.orient, a, sx, sy), bt = loco_beam(g.orient, a, tx, ty);
             const uint32_t cur = loco_sense(L.light, g.orient, bs, sx, sy);
             const uint32_t fut = loco_sense(L.light, g.orient, bt, tx, ty);
             const uint32_t li = (cur == fut) ? 2u : cur;     // (0,1)->0 (1,0)->1 else 2
-            p.aux = li * 48u | ((uint32_t)(bs + 1) << 8) | ((uint32_t)(bt + 1) << 16);
+            p.aux = li * 48u | ((uint32_t)(bs + 1) << 8) | ((uint32_t)(bt + 1) << 16) | (cur << 24) | (fut << 25);
         }
     }
     derive<BEH>(L, g, p);
@@ -259,28 +303,29 @@ __device__ __forceinline__ void evaluate(const Lat& L, const Geo& g, Prop& p) {
 template <int BEH, int RW>
 __device__ __forceinline__ bool probe_possible(const Lat& L, uint32_t idx, uint32_t d) {
     const uint32_t s = L.pos[idx];
-    const uint32_t t = (s + L.dirtab[8 + d]) & 0xffffu;
+    const uint32_t t = (s + L.dirtab[d].w) & 0xffffu;
     const uint32_t tr = t & 0xff, tc = t >> 8;
     if (BEH == SEP) return !Plane<RW>::bit(L.p2, tr, tc);
     return !(Plane<RW>::bit(L.p1, tr, tc) | Plane<RW>::bit(L.p0, tr, tc));
 }
 
 // --- commit of lane f's accepted proposal + incremental repair of every later lane --------------------
-// Lane f flips its two cells (fire-and-forget shared atomics) and rewrites its position.  Every lane then
-// patches its register windows with the flipped cells and re-derives; lanes that proposed the moved
-// particle itself (or, LOCO, that sense a rewritten beam) re-read the lattice.
+// Lane f flips its two cells (fire-and-forget shared reductions) and rewrites its position.  Every lane then
+// patches its register window with the flipped cells; a lane whose window really changed re-derives, a
+// lane that proposed the moved particle itself (or, LOCO, that senses a rewritten beam) re-reads the lattice.
 template <int BEH, int RW>
-__device__ __forceinline__ void commit_and_repair(const Lat& L, const Geo& g, uint32_t lane, uint32_t f, Prop& p) {
-    const uint32_t sf = __shfl_sync(0xffffffffu, p.s, f);
-    const uint32_t tf = __shfl_sync(0xffffffffu, p.t, f);
+__device__ __forceinline__ void commit_and_repair(const Lat& L, const Geo& g, uint32_t lane, uint32_t f, uint32_t sf, uint32_t ttf,
+                                                  bool active, Prop& p) {
+    const uint32_t tf = ttf & 0xffffu;
     uint32_t x = 1;                                          // plane bits flipped at both cells
     uint32_t wrote = 0;                                      // LOCO: rewritten beams (+1), 0 = none
+    const uint32_t sfr = sf & 0xff, sfc = sf >> 8, tfr = tf & 0xff, tfc = tf >> 8;
+    const bool mine = lane == f;
     if (BEH == SEP) {
-        // colour bits to flip: a move carries the mover's colour, a swap exchanges two colours
-        const uint32_t colf = __shfl_sync(0xffffffffu, p.aux, f);
+        // colour bits flipped at both cells: a move carries the mover's colour, a swap exchanges two colours
         const uint32_t kindf = __shfl_sync(0xffffffffu, p.kind, f);
         const uint32_t idxf = __shfl_sync(0xffffffffu, p.idx, f);
-        x = colf;
+        x = ttf >> 28;
         uint32_t partner = 0xffffffffu;
         if (kindf == 2) {
             // the partner's index: the reference's participants.iter().position scan (separation.rs:302),
@@ -290,51 +335,46 @@ __device__ __forceinline__ void commit_and_repair(const Lat& L, const Geo& g, ui
                 const uint32_t hit = __ballot_sync(0xffffffffu, i < g.n && L.pos[i] == tf);
                 if (hit) { partner = base + __ffs(hit) - 1; break; }
             }
-            x = colf ^ sep_colour(g, partner);
         }
-        if (lane == f) {
-            const uint32_t sr = sf & 0xff, sc = sf >> 8, tr = tf & 0xff, tc = tf >> 8;
-            if (x & 1) { Plane<RW>::atom_xor(L.p0, sr, sc); Plane<RW>::atom_xor(L.p0, tr, tc); }
-            if (x & 2) { Plane<RW>::atom_xor(L.p1, sr, sc); Plane<RW>::atom_xor(L.p1, tr, tc); }
+        if (mine) {
+            if (x & 1) { Plane<RW>::atom_xor(L.p0, sfr, sfc); Plane<RW>::atom_xor(L.p0, tfr, tfc); }
+            if (x & 2) { Plane<RW>::atom_xor(L.p1, sfr, sfc); Plane<RW>::atom_xor(L.p1, tfr, tfc); }
             L.pos[idxf] = (uint16_t)tf;
             if (kindf == 2) L.pos[partner] = (uint16_t)sf;
         }
     } else {
-        if (lane == f) {
-            const uint32_t sr = sf & 0xff, sc = sf >> 8, tr = tf & 0xff, tc = tf >> 8;
-            if (BEH == LOCO) {                               // locomotion.rs:344-519, net effect
-                const int sx = (int)sr - 1, sy = (int)sc - 1, tx = (int)tr - 1, ty = (int)tc - 1;
-                const int bs = (int)((p.aux >> 8) & 0xff) - 1, bt = (int)((p.aux >> 16) & 0xff) - 1;
-                const uint32_t cur = loco_sense(L.light, g.orient, bs, sx, sy);
-                const uint32_t fut = loco_sense(L.light, g.orient, bt, tx, ty);
-                if (cur) { L.light[bs] = (uint16_t)(sx | (sy << 8)); wrote = (uint32_t)(bs + 1); }
-                if (fut) { L.light[bt] = (uint16_t)(tx | (ty << 8)); wrote |= (uint32_t)(bt + 1) << 8; }
+        if (BEH == LOCO) {                                   // locomotion.rs:344-519, net effect
+            const uint32_t auxf = __shfl_sync(0xffffffffu, p.aux, f);
+            const uint32_t b1 = ((auxf >> 24) & 1u) ? ((auxf >> 8) & 0xff) : 0u;      // beam fronts lane f rewrites
+            const uint32_t b2 = ((auxf >> 25) & 1u) ? ((auxf >> 16) & 0xff) : 0u;
+            if (mine) {
+                if (b1) L.light[b1 - 1] = (uint16_t)((sfr - 2) | ((sfc - 2) << 8));
+                if (b2) L.light[b2 - 1] = (uint16_t)((tfr - 2) | ((tfc - 2) << 8));
             }
-            Plane<RW>::atom_xor(L.p0, sr, sc);
-            Plane<RW>::atom_xor(L.p0, tr, tc);
-            L.pos[p.idx] = (uint16_t)tf;
+            wrote = b1 | (b2 << 8);
         }
-        if (BEH == LOCO) wrote = __shfl_sync(0xffffffffu, wrote, f);
+        // addresses and masks are warp-uniform (sf, tf were broadcast); only lane f issues the three accesses
+        pred_xor_shared(mine, Plane<RW>::word(L.p0, sfr, sfc), 1u << (sfc & 31u));
+        pred_xor_shared(mine, Plane<RW>::word(L.p0, tfr, tfc), 1u << (tfc & 31u));
+        pred_store_u16(mine, L.pos + p.idx, tf);
     }
     __syncwarp();
-    // ---- repair (every lane; lanes <= f are finished and masked by the caller) ----
-    const uint32_t os = p.s - 0x0101u, ot = p.t - 0x0101u;
-    const uint32_t dS = win_bit(sf, os) ^ win_bit(tf, os);
-    const uint32_t dT = win_bit(sf, ot) ^ win_bit(tf, ot);
+    // ---- repair ----
+    const uint32_t dU = win25_patch(sf, tf - sf, 0, p.s - 0x0202u);
     bool reread = (p.s == sf);                               // the moved particle itself was proposed again
     if (BEH == SEP) {
-        if (x & 1) { p.S0 ^= dS; p.T0 ^= dT; }
-        if (x & 2) { p.S1 ^= dS; p.T1 ^= dT; }
+        if (x & 1) p.U0 ^= dU;
+        if (x & 2) p.U1 ^= dU;
         reread |= (p.s == tf);                               // the swap partner was proposed
     } else {
-        p.S0 ^= dS; p.T0 ^= dT;
+        p.U0 ^= dU;
         if (BEH == LOCO && wrote) {
             const uint32_t b1 = wrote & 0xff, b2 = wrote >> 8;
             const uint32_t bs = (p.aux >> 8) & 0xff, bt = (p.aux >> 16) & 0xff;
             reread |= (b1 && (bs == b1 || bt == b1)) || (b2 && (bs == b2 || bt == b2));
         }
     }
-    if (lane > f) {
+    if (active && lane > f && (dU != 0u || reread)) {
         if (reread) evaluate<BEH, RW>(L, g, p);
         else derive<BEH>(L, g, p);
     }
@@ -343,7 +383,7 @@ __device__ __forceinline__ void commit_and_repair(const Lat& L, const Geo& g, ui
 // --- commit rounds of one speculative batch ---------------------------------------------------------------
 // On entry every active lane holds a proposal evaluated against the current lattice; lane order = chain
 // order.  VERIFY: a repair that flips a lane's possible-ness changes how many draws that step consumes, so
-// the batch is cut at that lane (returned bound R; lanes >= R are not retired).
+// the batch is cut at that lane (returned bound R; lanes >= R are not retired).  ncommit is warp-uniform.
 template <int BEH, int RW, bool VERIFY>
 __device__ __forceinline__ uint32_t resolve_batch(const Lat& L, const Geo& g, uint32_t lane, bool active, Prop& p, uint32_t& ncommit) {
     uint32_t R = 32;
@@ -352,10 +392,12 @@ __device__ __forceinline__ uint32_t resolve_batch(const Lat& L, const Geo& g, ui
         if (VERIFY) A &= lowmask(R);
         if (!A) break;
         const uint32_t f = __ffs(A) - 1;
+        const uint32_t sf = __shfl_sync(0xffffffffu, p.s, f);
+        const uint32_t ttf = __shfl_sync(0xffffffffu, p.tt, f);
         const bool was = p.poss;
-        commit_and_repair<BEH, RW>(L, g, lane, f, p);
-        if (lane <= f || !active) p.eff = false;
-        if (lane == f) ++ncommit;
+        commit_and_repair<BEH, RW>(L, g, lane, f, sf, ttf, active, p);
+        p.eff = p.eff && lane != f;
+        ++ncommit;
         if (VERIFY) {
             const uint32_t X = __ballot_sync(0xffffffffu, active && lane > f && p.poss != was) & lowmask(R);
             if (X) R = (uint32_t)__ffs(X) - 1;
@@ -367,13 +409,11 @@ __device__ __forceinline__ uint32_t resolve_batch(const Lat& L, const Geo& g, ui
 // --- initial configuration ---------------------------------------------------------------------------
 template <int BEH, int RW>
 __device__ __forceinline__ uint32_t init_instance(const KParams& P, const Lat& L, const Geo& g, const Instance& in, uint32_t lane) {
-    const uint32_t G = g.G, a = g.a, PG = G + 2;
+    const uint32_t G = g.G, a = g.a, PG = G + 4;
     uint32_t* pstat = (BEH == SEP) ? L.p2 : L.p1;
-    // zero every plane including its two guard rows
-    const int guarded = (int)P.plane_words + 2 * RW;
-    for (int w = (int)lane; w < guarded; w += 32) {
-        L.p0[w - RW] = 0; L.p1[w - RW] = 0;
-        if (BEH == SEP || BEH == COAT) L.p2[w - RW] = 0;
+    for (uint32_t w = lane; w < P.plane_words; w += 32) {
+        L.p0[w] = 0; L.p1[w] = 0;
+        if (BEH == SEP || BEH == COAT) L.p2[w] = 0;
     }
     __syncwarp();
     // static "not enterable" mask: everything except arena cells |i - j| <= a (mod.rs:115-122)
@@ -381,9 +421,9 @@ __device__ __forceinline__ uint32_t init_instance(const KParams& P, const Lat& L
 #pragma unroll
         for (int w = 0; w < RW; ++w) {
             uint32_t m = 0xffffffffu;
-            if (r >= 1 && r <= G) {
-                int lo = (int)r - (int)a; if (lo < 1) lo = 1;
-                int hi = (int)r + (int)a; if (hi > (int)G) hi = (int)G;
+            if (r >= 2 && r <= G + 1) {
+                int lo = (int)r - (int)a; if (lo < 2) lo = 2;
+                int hi = (int)r + (int)a; if (hi > (int)G + 1) hi = (int)G + 1;
                 lo -= 32 * w; hi -= 32 * w;
                 if (lo < 0) lo = 0;
                 if (hi > 31) hi = 31;
@@ -397,7 +437,7 @@ __device__ __forceinline__ uint32_t init_instance(const KParams& P, const Lat& L
     }
     __syncwarp();
     if (BEH == COAT) {                                       // object hexagon, coating.rs:261-284
-        uint32_t o = in.layers, c = in.coat, side = 2 * o + 1, base = a - o + c + 1;   // +1: padded
+        uint32_t o = in.layers, c = in.coat, side = 2 * o + 1, base = a - o + c + 2;   // +2: padded
         for (uint32_t k = lane; k < side * side; k += 32) {
             uint32_t u = k / side, v = k % side;
             int dd = (int)u - (int)v;
@@ -425,7 +465,7 @@ __device__ __forceinline__ uint32_t init_instance(const KParams& P, const Lat& L
             uint64_t vj = (uint64_t)w[4 * k + 2] | ((uint64_t)w[4 * k + 3] << 32);
             rej |= (vi * G > zone) | (vj * G > zone);
             uint32_t i = (uint32_t)__umul64hi(vi, (uint64_t)G), j = (uint32_t)__umul64hi(vj, (uint64_t)G);
-            cand[k] = (i + 1) | ((j + 1) << 8);
+            cand[k] = (i + 2) | ((j + 2) << 8);
         }
         if (__any_sync(0xffffffffu, rej)) status = 1;        // Uniform zone rejection (p ~ G/2^64): not replayed
         uint32_t c01 = cand[0] | (cand[1] << 16), c23 = cand[2] | (cand[3] << 16);
@@ -470,7 +510,7 @@ __device__ __forceinline__ uint32_t init_instance(const KParams& P, const Lat& L
         __syncwarp();
         for (uint32_t k = lane; k < g.n; k += 32) {
             uint32_t cell = L.pos[k];
-            int x = (int)(cell & 0xff) - 1, y = (int)(cell >> 8) - 1;
+            int x = (int)(cell & 0xff) - 2, y = (int)(cell >> 8) - 2;
             int b; uint32_t val, keyv;
             if (o == 1) { b = 2 * x - y; val = (uint32_t)y; keyv = ((uint32_t)y << 8) | (uint32_t)x; }
             else if (o == 2) { b = 2 * y - x; val = (uint32_t)x; keyv = ((uint32_t)x << 8) | (uint32_t)y; }
@@ -511,7 +551,7 @@ __device__ __forceinline__ void fitness(const KParams& P, const Lat& L, const Ge
         if (BEH == AGG || BEH == LOCO) {
             s0 += __popc(win9<RW>(L.p0, r, c) & NB_MASK);                       // mod.rs:166-178
             if (BEH == LOCO) {
-                int x = (int)r - 1, y = (int)c - 1;
+                int x = (int)r - 2, y = (int)c - 2;
                 s1 += g.orient == 1 ? (uint32_t)y : g.orient == 2 ? (uint32_t)x : (uint32_t)(x - y + (int)g.a);
             }
         } else if (BEH == SEP) {
@@ -519,7 +559,7 @@ __device__ __forceinline__ void fitness(const KParams& P, const Lat& L, const Ge
             s0 += __popc((w0 | w1) & NB_MASK);                                  // separation.rs:255-275
             s1 += __popc(same_mask(w0, w1, sep_colour(g, k)) & NB_MASK);
         } else {
-            uint32_t dv = P.coat_dist[in.aux + (r - 1) * g.G + (c - 1)];        // coating.rs:561-574
+            uint32_t dv = P.coat_dist[in.aux + (r - 2) * g.G + (c - 2)];        // coating.rs:561-574
             if (dv != 0xFFFFu) s1 += dv;
         }
     }
@@ -542,7 +582,7 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
     const uint64_t steps = in.steps, ms = in.move_seed;
     const uint32_t n = g.n;
     uint64_t nposs = 0;                                      // per lane
-    uint32_t ncommit = 0;                                    // per lane
+    uint32_t ncommit = 0;                                    // warp-uniform
 
     if (MODE == MODE_FAST) {
         // Every batch retires 32 consecutive steps; the random numbers of batch b+1 do not depend on the
@@ -627,7 +667,6 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
         uint32_t mid = __reduce_add_sync(0xffffffffu, (uint32_t)((nposs >> 24) & 0xffffffu));
         uint32_t hi = __reduce_add_sync(0xffffffffu, (uint32_t)(nposs >> 48));
         nposs = (uint64_t)lo + ((uint64_t)mid << 24) + ((uint64_t)hi << 48);
-        ncommit = __reduce_add_sync(0xffffffffu, ncommit);
     }
 
     uint32_t i0, i1;
@@ -659,10 +698,11 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
 template <int BEH, int RW, int MODE>
 __global__ void __launch_bounds__(256) sops_chain_kernel(const KParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
-    __shared__ uint32_t s_dirtab[16];
-    if (threadIdx.x < 6) {
-        s_dirtab[threadIdx.x] = dir_word((int)threadIdx.x);
-        s_dirtab[8 + threadIdx.x] = (uint32_t)dir_delta((int)threadIdx.x);
+    __shared__ uint4 s_dirtab[8];
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int d = 0; d < 6; ++d)
+            s_dirtab[d] = make_uint4(dir_back5(d), dir_mid5(d), dir_front5(d), ((uint32_t)dir_delta(d) & 0xffffu) | (dir_tbit(d) << 16) | (dir_code(d) << 24));
     }
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
