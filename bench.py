@@ -28,6 +28,9 @@ SIZES_C2 = [(6, 4), (10, 7), (13, 9)]
 SEEDS_C2 = [1, 2, 3, 4, 5]
 POP_C2 = 50
 GENOME_SEED = 0x45766F534F5053          # "EvoSOPS" 
+# the reference's evolved aggregation genome (misc_scripts/genome_agg_compare.py:1), data only
+EVOLVED_AGG = [4, 0, 0, 1, 6, 1, 0, 0, 1, 6, 10, 0, 7, 1, 2, 2, 3, 1, 0, 1, 4, 9, 5, 0,
+               6, 1, 2, 0, 10, 10, 0, 1, 10, 2, 9, 8, 8, 7, 3, 0, 9, 9, 7, 8, 7, 4, 7, 2]
 
 
 def splitmix64(state):
@@ -259,6 +262,22 @@ def main():
         ctx.collect()
         v_o = reduce(attempts_step, dist.ReduceOp.SUM if world > 1 else None) / (reduce(ms_o, dist.ReduceOp.MAX if world > 1 else None) * 1e-3)
         extra["verify_mode" if other == E.RNG_VERIFY else "fast_mode"] = {"value": v_o, "unit": "attempts/s", "ms_per_step": ms_o}
+        # a late-generation population: +-1 mutants of the reference's evolved genome (what the GA converges to);
+        # same batch shape as the headline, far fewer accepted moves per chain
+        evo = np.tile(np.asarray(EVOLVED_AGG, dtype=np.uint8), (POP_C2, 1))
+        for g in range(1, POP_C2):
+            st = (GENOME_SEED ^ (0x9E3779B97F4A7C15 * (rank * POP_C2 + g))) & 0xFFFFFFFFFFFFFFFF
+            for _ in range(3):
+                st, z = splitmix64(st)
+                k = z % 48
+                evo[g, k] = min(args.gran, max(0, int(evo[g, k]) + (1 if (z >> 32) & 1 else -1)))
+        ctx.prepare(E.AGG, evo, tsz, tsd, gran=args.gran, rng_mode=mode)
+        ctx.launch(); ctx.sync()
+        ctx.launch(); ms_e = ctx.sync()
+        res_e = ctx.collect()
+        v_e = reduce(attempts_step, dist.ReduceOp.SUM if world > 1 else None) / (reduce(ms_e, dist.ReduceOp.MAX if world > 1 else None) * 1e-3)
+        extra["evolved_population"] = {"value": v_e, "unit": "attempts/s", "ms_per_step": ms_e,
+                                       "mean_fitness": float(res_e["norm"].mean())}
         n_sweep, cap = 50000, 200000
         seeds = list(range(1 + rank * n_sweep, 1 + (rank + 1) * n_sweep))
         for nm, md in (("fast", E.RNG_FAST), ("verify", E.RNG_VERIFY)):
