@@ -62,7 +62,7 @@ struct KParams {
     uint32_t plane_words, pos_words;
 };
 
-#define SOPS_LIGHT_WORDS 32u        // 64 u16 beams (a <= 30 -> 2a+1 <= 61)
+#define SOPS_LIGHT_WORDS 32u        // 64 u16 beams (a <= 29 -> 2a+1 <= 59)
 
 // ---------------------------------------------------------------------- direction tables --------
 // Directions in the reference's order (mod.rs:80-82): (-1,0) (1,0) (0,-1) (0,1) (-1,-1) (1,1).

@@ -168,3 +168,51 @@ def test_results_independent_of_batch_composition(ctx, genomes):
         for t in range(3):
             one = ctx.eval_batch(E.AGG, gs[g], [sizes[t]], [seeds[t]], rng_mode=E.RNG_FAST)
             assert one[0, 0]["i0"] == full[g, t]["i0"]
+
+
+def test_fast_mode_matches_verify_mode_distribution_ks(ctx, genomes):
+    # north_star: "in fast mode (Philox) fitness distributions over >= 1000 seeds must match within a stated
+    # KS-test tolerance".  1024 move seeds per mode and size, full chains, two-sample KS p > 1e-3 on the edge counts;
+    # verify mode is itself bit-exact against the oracle's WyRand restatement (tests above).
+    from scipy.stats import ks_2samp
+    for size, name in (((6, 3), "agg_evolved"), ((10, 7), "agg_theory")):
+        flags = E.F_THEORY_TABLE if name == "agg_theory" else 0
+        ms_a = np.arange(1, 1025, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+        ms_b = np.arange(5001, 6025, dtype=np.uint64) * np.uint64(0xD1B54A32D192ED03)
+        a = ctx.eval_batch(E.AGG, genomes[name], [size] * 1024, [62813] * 1024, rng_mode=E.RNG_VERIFY, move_seeds=ms_a, flags=flags)
+        b = ctx.eval_batch(E.AGG, genomes[name], [size] * 1024, [62813] * 1024, rng_mode=E.RNG_FAST, move_seeds=ms_b, flags=flags)
+        res = ks_2samp(a["i0"].reshape(-1), b["i0"].reshape(-1))
+        assert res.pvalue > 1e-3, (size, res)
+        assert abs(a["norm"].mean() - b["norm"].mean()) < 0.01
+
+
+def test_theory_genome_quality_matches_published_line(ctx, genomes):
+    # authors' dashed reference line for the theory aggregation algorithm: 0.92 (misc_scripts/plotter_single_agg.py:92)
+    ms = np.arange(1, 257, dtype=np.uint64) * np.uint64(2654435761)
+    r = ctx.eval_batch(E.AGG, genomes["agg_theory"], [(13, 9)] * 256, [62813] * 256, rng_mode=E.RNG_FAST, move_seeds=ms,
+                       flags=E.F_THEORY_TABLE)
+    assert 0.90 < r["norm"].mean() < 0.94
+
+
+def test_results_identical_across_device_counts(genomes):
+    # streams are keyed by the global instance, never by device -> any device count gives the same bits
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    gs = np.stack([genomes["agg_evolved"], genomes["agg_random"], genomes["agg_theory"].clip(0, 5)])
+    sizes = [(6, 3), (10, 7), (13, 9), (20, 14)]
+    seeds = [1, 2, 3, 4]
+    one, two = E.Context(device_ids=[0]), E.Context(device_ids=[0, 1])
+    try:
+        for mode in (E.RNG_VERIFY, E.RNG_FAST):
+            a = one.eval_batch(E.AGG, gs, sizes, seeds, rng_mode=mode, steps_override=300000, flags=E.F_DUMP)
+            b = two.eval_batch(E.AGG, gs, sizes, seeds, rng_mode=mode, steps_override=300000, flags=E.F_DUMP)
+            assert np.array_equal(a, b)
+            for q in range(12):
+                G, n, _ = E.instance_shape(E.AGG, sizes[q % 4])
+                ga, pa = one.dump_state(q, G, n)
+                gb, pb = two.dump_state(q, G, n)
+                assert np.array_equal(ga, gb) and np.array_equal(pa, pb)
+    finally:
+        one.close()
+        two.close()
