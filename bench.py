@@ -271,13 +271,19 @@ def main():
                 st, z = splitmix64(st)
                 k = z % 48
                 evo[g, k] = min(args.gran, max(0, int(evo[g, k]) + (1 if (z >> 32) & 1 else -1)))
-        ctx.prepare(E.AGG, evo, tsz, tsd, gran=args.gran, rng_mode=mode)
-        ctx.launch(); ctx.sync()
-        ctx.launch(); ms_e = ctx.sync()
-        res_e = ctx.collect()
-        v_e = reduce(attempts_step, dist.ReduceOp.SUM if world > 1 else None) / (reduce(ms_e, dist.ReduceOp.MAX if world > 1 else None) * 1e-3)
-        extra["evolved_population"] = {"value": v_e, "unit": "attempts/s", "ms_per_step": ms_e,
-                                       "mean_fitness": float(res_e["norm"].mean())}
+        best = None
+        for kname, kflag in (("warp", 0), ("cta4", E.F_FORCE_CTA)):
+            ctx.prepare(E.AGG, evo, tsz, tsd, gran=args.gran, rng_mode=mode, flags=kflag)
+            ctx.launch(); ctx.sync()
+            ctx.launch(); ms_e = ctx.sync()
+            res_e = ctx.collect()
+            ms_e = reduce(ms_e, dist.ReduceOp.MAX if world > 1 else None)
+            if best is None or ms_e < best[0]:
+                best = (ms_e, kname, float(res_e["norm"].mean()))
+            extra.setdefault("evolved_population", {})["ms_per_step_" + kname] = ms_e
+        v_e = reduce(attempts_step, dist.ReduceOp.SUM if world > 1 else None) / (best[0] * 1e-3)
+        extra["evolved_population"].update({"value": v_e, "unit": "attempts/s", "ms_per_step": best[0], "kernel": best[1],
+                                            "generations_per_s": 1e3 / best[0], "mean_fitness": best[2]})
         n_sweep, cap = 50000, 200000
         seeds = list(range(1 + rank * n_sweep, 1 + (rank + 1) * n_sweep))
         for nm, md in (("fast", E.RNG_FAST), ("verify", E.RNG_VERIFY)):

@@ -4,7 +4,8 @@ Layout: csrc/ (sm_100a CUDA kernels + the C ABI of include/evosops.h), capi.py (
 sops_core.py (host mirror of the reference's SOPSCore module API), sharding.py (one-process-per-GPU
 partitioning of a population).  Nothing here imports oracle/."""
 from .capi import (AGG, SEP, COAT, LOCO, RNG_VERIFY, RNG_FAST, F_DUMP, F_INIT_ONLY, F_THEORY_TABLE,  # noqa: F401
+                   F_FORCE_WARP, F_FORCE_CTA,
                    GENOME_LEN, GENOME_SHAPE, Context, SopsError, instance_shape, coat_distance_grid)
 
-__all__ = ["AGG", "SEP", "COAT", "LOCO", "RNG_VERIFY", "RNG_FAST", "F_DUMP", "F_INIT_ONLY", "F_THEORY_TABLE",
+__all__ = ["AGG", "SEP", "COAT", "LOCO", "RNG_VERIFY", "RNG_FAST", "F_DUMP", "F_INIT_ONLY", "F_THEORY_TABLE", "F_FORCE_WARP", "F_FORCE_CTA",
            "GENOME_LEN", "GENOME_SHAPE", "Context", "SopsError", "instance_shape", "coat_distance_grid"]

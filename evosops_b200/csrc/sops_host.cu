@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -101,6 +102,7 @@ struct Group {                      // one kernel launch: instances of one row-w
     uint32_t dump_stride;
     size_t dump_off;                // word offset of this group's dump area
     int wpb, blocks;
+    int cta_w;                      // 0: warp-per-instance kernel; else warps per instance of the CTA kernel
     size_t smem;
 };
 
@@ -190,6 +192,15 @@ template <int BEH>
 kernel_fn pick_kernel(int rw, int mode) {
     if (rw == 1) return mode == 0 ? sops::sops_chain_kernel<BEH, 1, 0> : sops::sops_chain_kernel<BEH, 1, 1>;
     return mode == 0 ? sops::sops_chain_kernel<BEH, 2, 0> : sops::sops_chain_kernel<BEH, 2, 1>;
+}
+// CTA-per-chain variant: 4 warps per chain (opt-in, SOPS_F_FORCE_CTA; see DESIGN.md for when it pays)
+kernel_fn kernel_for_cta(int beh, int rw) {
+    switch (beh) {
+    case SOPS_AGG: return rw == 1 ? sops::sops_chain_cta_kernel<sops::AGG, 1, 4> : sops::sops_chain_cta_kernel<sops::AGG, 2, 4>;
+    case SOPS_SEP: return rw == 1 ? sops::sops_chain_cta_kernel<sops::SEP, 1, 4> : sops::sops_chain_cta_kernel<sops::SEP, 2, 4>;
+    case SOPS_COAT: return rw == 1 ? sops::sops_chain_cta_kernel<sops::COAT, 1, 4> : sops::sops_chain_cta_kernel<sops::COAT, 2, 4>;
+    default: return rw == 1 ? sops::sops_chain_cta_kernel<sops::LOCO, 1, 4> : sops::sops_chain_cta_kernel<sops::LOCO, 2, 4>;
+    }
 }
 kernel_fn kernel_for(int beh, int rw, int mode) {
     switch (beh) {
@@ -436,23 +447,37 @@ int sops_batch_prepare(sops_ctx* ctx, int behavior, const uint8_t* genomes, uint
             layout_group(grp, behavior, max_pg, max_n);
             grp.dump_off = dump_words;
             if (flags & SOPS_F_DUMP) dump_words += (size_t)grp.count * grp.dump_stride;
-            // launch geometry: spread few instances over all SMs, otherwise fill the machine with
-            // 8-warp CTAs that pull instances from a work counter
-            kernel_fn fn = kernel_for(behavior, grp.rw, rng_mode);
+            // kernel choice: one warp per chain, unless the caller asks for the 4-warp CTA-per-chain variant
+            // (fast mode only; it pays when few chains with very low acceptance run, i.e. late GA generations)
             const size_t smem_per_warp = (size_t)grp.words_per_warp * 4;
-            int wpb = 8;
-            if (grp.count <= 8u * (uint32_t)d.n_sm) wpb = (int)((grp.count + (uint32_t)d.n_sm - 1) / (uint32_t)d.n_sm);
-            if (wpb < 1) wpb = 1;
-            grp.wpb = wpb;
-            grp.smem = smem_per_warp * (size_t)wpb;
-            if (grp.smem > 48 * 1024)
-                CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grp.smem));
+            grp.cta_w = (rng_mode == SOPS_RNG_FAST && (flags & SOPS_F_FORCE_CTA) && !(flags & SOPS_F_FORCE_WARP)) ? 4 : 0;
             int per_sm = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, wpb * 32, grp.smem));
-            if (per_sm < 1) return fail(ctx, SOPS_E_UNSUPPORTED, "instance does not fit in shared memory");
-            uint32_t want = (grp.count + (uint32_t)wpb - 1) / (uint32_t)wpb;
-            uint32_t cap = (uint32_t)per_sm * (uint32_t)d.n_sm;
-            grp.blocks = (int)std::min(want, cap);
+            if (grp.cta_w) {
+                kernel_fn fn = kernel_for_cta(behavior, grp.rw);
+                grp.wpb = grp.cta_w;
+                grp.smem = smem_per_warp;
+                if (grp.smem > 48 * 1024)
+                    CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grp.smem));
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, grp.cta_w * 32, grp.smem));
+                if (per_sm < 1) return fail(ctx, SOPS_E_UNSUPPORTED, "instance does not fit in shared memory");
+                grp.blocks = (int)std::min(grp.count, (uint32_t)per_sm * (uint32_t)d.n_sm);
+            } else {
+                // launch geometry: spread few instances over all SMs, otherwise fill the machine with
+                // 8-warp CTAs that pull instances from a work counter
+                kernel_fn fn = kernel_for(behavior, grp.rw, rng_mode);
+                int wpb = 8;
+                if (grp.count <= 8u * (uint32_t)d.n_sm) wpb = (int)((grp.count + (uint32_t)d.n_sm - 1) / (uint32_t)d.n_sm);
+                if (wpb < 1) wpb = 1;
+                grp.wpb = wpb;
+                grp.smem = smem_per_warp * (size_t)wpb;
+                if (grp.smem > 48 * 1024)
+                    CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grp.smem));
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, wpb * 32, grp.smem));
+                if (per_sm < 1) return fail(ctx, SOPS_E_UNSUPPORTED, "instance does not fit in shared memory");
+                uint32_t want = (grp.count + (uint32_t)wpb - 1) / (uint32_t)wpb;
+                uint32_t cap = (uint32_t)per_sm * (uint32_t)d.n_sm;
+                grp.blocks = (int)std::min(want, cap);
+            }
             d.groups.push_back(grp);
         }
         CK(grow_dev(&d.d_inst, &d.cap_inst, (size_t)d.n_inst));
@@ -506,7 +531,7 @@ int sops_batch_launch(sops_ctx* ctx) {
             kp.off_p0 = g.off_p0; kp.off_p1 = g.off_p1; kp.off_p2 = g.off_p2;
             kp.off_pos = g.off_pos; kp.off_thr = g.off_thr; kp.off_aux = g.off_aux;
             kp.plane_words = g.plane_words; kp.pos_words = g.pos_words;
-            kernel_fn fn = kernel_for(ctx->behavior, g.rw, ctx->rng_mode);
+            kernel_fn fn = g.cta_w ? kernel_for_cta(ctx->behavior, g.rw) : kernel_for(ctx->behavior, g.rw, ctx->rng_mode);
             fn<<<g.blocks, g.wpb * 32, g.smem, d.stream>>>(kp);
             CK(cudaGetLastError());
             ++ctx->launches;

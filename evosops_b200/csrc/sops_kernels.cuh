@@ -723,4 +723,210 @@ __global__ void __launch_bounds__(256) sops_chain_kernel(const KParams P) {
     }
 }
 
+// =========================================================================================================
+// CTA-per-instance variant (fast mode): W warps speculate on 32*W consecutive steps of ONE chain.
+// Used when a batch has far fewer instances than the GPU has warp slots (a GA generation: a few hundred
+// chains): the per-batch cost (draws, window loads, decision) is paid once per 32*W steps instead of once
+// per 32, and the otherwise idle schedulers of the SM work on the same chain.  Commits stay strictly
+// ordered: the lowest accepted (warp, lane) publishes its move in shared memory and commits, the block
+// synchronises, every later thread patches its register window (same arithmetic as the warp kernel), and a
+// `__syncthreads_or` tells everyone whether any decision changed (then the accepted sets are re-voted).
+// The retired sequence is exactly the sequential chain, and — being keyed by step index — bit-identical to
+// the warp-per-instance kernel.
+// =========================================================================================================
+template <int BEH>
+__device__ __forceinline__ bool patch_window(uint32_t sf, uint32_t ttf, uint32_t wrote, Prop& p, bool& reread) {
+    const uint32_t tf = ttf & 0xffffu;
+    const uint32_t dU = win25_patch(sf, tf - sf, 0, p.s - 0x0202u);
+    reread = (p.s == sf);                                    // the moved particle itself was proposed again
+    if (BEH == SEP) {
+        const uint32_t x = ttf >> 28;
+        if (x & 1) p.U0 ^= dU;
+        if (x & 2) p.U1 ^= dU;
+        reread |= (p.s == tf);                               // the swap partner was proposed
+    } else {
+        p.U0 ^= dU;
+        if (BEH == LOCO && wrote) {
+            const uint32_t b1 = wrote & 0xff, b2 = wrote >> 8;
+            const uint32_t bs = (p.aux >> 8) & 0xff, bt = (p.aux >> 16) & 0xff;
+            reread |= (b1 && (bs == b1 || bt == b1)) || (b2 && (bs == b2 || bt == b2));
+        }
+    }
+    return dU != 0u || reread;
+}
+
+template <int BEH, int RW, int W>
+__device__ __forceinline__ void resolve_cta(const Lat& L, const Geo& g, uint32_t tid, bool active, Prop& p, uint32_t& ncommit,
+                                            uint32_t* s_ballot /*[W], this super-batch's buffer*/, uint32_t* s_bc /*[8]*/) {
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+    {
+        const uint32_t mine = __ballot_sync(0xffffffffu, p.eff);
+        if (lane == 0) s_ballot[warp] = mine;
+    }
+    __syncthreads();                                         // S1: every thread evaluated; accepted sets published
+    uint32_t A[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) A[w] = s_ballot[w];
+    for (;;) {
+        // lowest pending accepted (warp, lane): identical in every thread
+        uint32_t wsel = W, Aw = 0;
+#pragma unroll
+        for (int w = W - 1; w >= 0; --w) if (A[w]) { wsel = (uint32_t)w; Aw = A[w]; }
+        if (wsel == W) break;
+        const uint32_t f = __ffs(Aw) - 1, gidx = wsel * 32 + f;
+#pragma unroll
+        for (int w = 0; w < W; ++w) if ((uint32_t)w == wsel) A[w] = Aw & (Aw - 1);
+        const bool mine = tid == gidx;
+        ++ncommit;
+        if (mine) {
+            s_bc[0] = p.s; s_bc[1] = p.tt;
+            if (BEH == SEP) { s_bc[2] = p.kind; s_bc[3] = p.idx; }
+            if (BEH == LOCO) {                               // locomotion.rs:344-519, net effect
+                const uint32_t b1 = ((p.aux >> 24) & 1u) ? ((p.aux >> 8) & 0xff) : 0u;
+                const uint32_t b2 = ((p.aux >> 25) & 1u) ? ((p.aux >> 16) & 0xff) : 0u;
+                const uint32_t sr = p.s & 0xff, sc = p.s >> 8, tr = p.t & 0xff, tc = p.t >> 8;
+                if (b1) L.light[b1 - 1] = (uint16_t)((sr - 2) | ((sc - 2) << 8));
+                if (b2) L.light[b2 - 1] = (uint16_t)((tr - 2) | ((tc - 2) << 8));
+                s_bc[2] = b1 | (b2 << 8);
+            }
+            if (BEH != SEP) {
+                const uint32_t sr = p.s & 0xff, sc = p.s >> 8, tr = p.t & 0xff, tc = p.t >> 8;
+                Plane<RW>::atom_xor(L.p0, sr, sc);
+                Plane<RW>::atom_xor(L.p0, tr, tc);
+                L.pos[p.idx] = (uint16_t)p.t;
+            }
+            p.eff = false;
+        }
+        __syncthreads();                                     // S2: the move (and, non-SEP, the lattice update) is visible
+        const uint32_t sf = s_bc[0], ttf = s_bc[1];
+        const uint32_t wrote = (BEH == LOCO) ? s_bc[2] : 0u;
+        if (BEH == SEP) {
+            const uint32_t kindf = s_bc[2], tf = ttf & 0xffffu, x = ttf >> 28;
+            if (kindf == 2) {                                // partner index: block-wide scan of the position list
+                for (uint32_t i = tid; i < g.n; i += 32 * W) if (L.pos[i] == tf) s_bc[4] = i;
+                __syncthreads();
+            }
+            if (mine) {
+                const uint32_t sr = sf & 0xff, sc = sf >> 8, tr = tf & 0xff, tc = tf >> 8;
+                if (x & 1) { Plane<RW>::atom_xor(L.p0, sr, sc); Plane<RW>::atom_xor(L.p0, tr, tc); }
+                if (x & 2) { Plane<RW>::atom_xor(L.p1, sr, sc); Plane<RW>::atom_xor(L.p1, tr, tc); }
+                if (kindf == 2) L.pos[s_bc[4]] = (uint16_t)sf;
+                L.pos[s_bc[3]] = (uint16_t)tf;
+            }
+        }
+        bool reread;
+        const bool touched = patch_window<BEH>(sf, ttf, wrote, p, reread) && active && tid > gidx;
+        if (__syncthreads_or(touched)) {                     // S3
+            if (touched) {
+                if (reread) evaluate<BEH, RW>(L, g, p);
+                else derive<BEH>(L, g, p);
+            }
+            const uint32_t again = __ballot_sync(0xffffffffu, p.eff);
+            if (lane == 0) s_ballot[warp] = again;
+            __syncthreads();                                 // S4
+#pragma unroll
+            for (int w = 0; w < W; ++w) A[w] = s_ballot[w];
+        }
+    }
+}
+
+template <int BEH, int RW, int W>
+__global__ void __launch_bounds__(32 * W) sops_chain_cta_kernel(const KParams P) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ uint4 s_dirtab[8];
+    __shared__ uint32_t s_ballot[2][8];
+    __shared__ uint32_t s_bc[8];
+    __shared__ uint32_t s_q;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int d = 0; d < 6; ++d)
+            s_dirtab[d] = make_uint4(dir_back5(d), dir_mid5(d), dir_front5(d), ((uint32_t)dir_delta(d) & 0xffffu) | (dir_tbit(d) << 16) | (dir_code(d) << 24));
+    }
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    Lat L;
+    L.p0 = smem + P.off_p0; L.p1 = smem + P.off_p1; L.p2 = smem + P.off_p2;
+    L.pos = reinterpret_cast<uint16_t*>(smem + P.off_pos);
+    L.thr = reinterpret_cast<uint16_t*>(smem + P.off_thr);
+    L.light = reinterpret_cast<uint16_t*>(smem + P.off_aux);
+    L.dirtab = s_dirtab;
+    for (;;) {
+        __syncthreads();                                     // previous instance fully retired (s_q, lattice reusable)
+        if (tid == 0) s_q = atomicAdd(P.work_counter, 1u);
+        __syncthreads();
+        const uint32_t q = s_q;
+        if (q >= P.n_inst) break;
+        const Instance in = P.inst[q];
+        Geo g;
+        g.a = in.arena; g.G = 2 * g.a + 1; g.orient = in.orient;
+        {
+            uint32_t p = in.layers, t = p + in.coat;
+            g.n = BEH == AGG ? 3 * p * (p + 1) + 1 : BEH == COAT ? 3 * t * (t + 1) - 3 * p * (p + 1) : 3 * p * (p + 1);
+        }
+        g.n3 = g.n / 3;
+        uint32_t status = 0;
+        if (warp == 0) status = init_instance<BEH, RW>(P, L, g, in, lane);
+        __syncthreads();
+
+        const uint64_t steps = in.steps, ms = in.move_seed;
+        const uint32_t n = g.n;
+        const uint32_t key = (uint32_t)ms, khi = (uint32_t)(ms >> 32);
+        auto draw = [&](uint64_t st, Prop& qd) {
+            uint32_t r0, r1;
+            philox2x32_10((uint32_t)st, (uint32_t)(st >> 32) ^ khi, key, r0, r1);
+            qd.idx = __umulhi(r0, n);
+            const uint64_t m6 = (uint64_t)r1 * 6u;
+            qd.d = (uint32_t)(m6 >> 32);
+            qd.pd = __umulhi((uint32_t)m6, 1000u);
+        };
+        uint64_t nposs = 0;
+        uint32_t ncommit = 0;
+        const uint64_t nsuper = (steps + 32 * W - 1) / (32 * W);
+        Prop cur;
+        draw((uint64_t)tid, cur);
+        for (uint64_t b = 0; b < nsuper; ++b) {
+            const uint64_t st = b * (32 * W) + tid;
+            const bool active = st < steps;
+            Prop nxt;
+            draw(st + 32 * W, nxt);
+            evaluate<BEH, RW>(L, g, cur);
+            if (!active) { cur.eff = false; cur.poss = false; }
+            resolve_cta<BEH, RW, W>(L, g, tid, active, cur, ncommit, s_ballot[b & 1], s_bc);
+            nposs += (active && cur.poss) ? 1u : 0u;
+            cur.idx = nxt.idx; cur.d = nxt.d; cur.pd = nxt.pd;
+        }
+        {
+            uint32_t lo = __reduce_add_sync(0xffffffffu, (uint32_t)(nposs & 0xffffffu));
+            uint32_t mid = __reduce_add_sync(0xffffffffu, (uint32_t)((nposs >> 24) & 0xffffffu));
+            uint32_t hi = __reduce_add_sync(0xffffffffu, (uint32_t)(nposs >> 48));
+            nposs = (uint64_t)lo + ((uint64_t)mid << 24) + ((uint64_t)hi << 48);
+            if (lane == 0) atomicAdd(&P.counters[1], (unsigned long long)nposs);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t i0, i1;
+            fitness<BEH, RW>(P, L, g, in, lane, i0, i1);
+            if (lane == 0) {
+                DevResult r; r.i0 = i0; r.i1 = i1; r.i2 = (BEH == LOCO) ? g.orient : 0u; r.status = status;
+                P.out[in.slot] = r;
+                atomicAdd(&P.counters[0], (unsigned long long)steps);
+                atomicAdd(&P.counters[2], (unsigned long long)ncommit);
+            }
+            if (P.dump) {
+                uint32_t* dst = P.dump + (size_t)(in.slot - P.dump_slot0) * P.dump_stride;
+                const uint32_t pw = P.plane_words;
+                for (uint32_t w = lane; w < pw; w += 32) {
+                    dst[w] = L.p0[w]; dst[pw + w] = L.p1[w];
+                    dst[2 * pw + w] = (BEH == SEP || BEH == COAT) ? L.p2[w] : 0u;
+                }
+                const uint32_t* pos32 = reinterpret_cast<const uint32_t*>(L.pos);
+                for (uint32_t w = lane; w < (g.n + 1) / 2; w += 32) dst[3 * pw + w] = pos32[w];
+                if (BEH == LOCO) {
+                    const uint32_t* l32 = reinterpret_cast<const uint32_t*>(L.light);
+                    dst[3 * pw + P.pos_words + lane] = l32[lane];
+                }
+            }
+        }
+    }
+}
+
 }  // namespace sops

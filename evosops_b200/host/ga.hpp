@@ -194,7 +194,13 @@ public:
             std::vector<uint8_t> orient;
             if (spec_.behavior == Loco) { orient.resize(todo.size() * T); for (auto& o : orient) o = (uint8_t)rng_.inclusive(1, 3); }   // locomotion.rs:109
             std::vector<sops_result> out;
-            ev_.eval(spec_.behavior, flat, (uint32_t)todo.size(), trials, granularity_, w1_, w2_, ms, orient, 0, 0, out);
+            // kernel hint (ours): late generations accept < 1 % of attempts; there the 4-warp-per-chain kernel
+            // is ~1.3x faster.  Results do not depend on the choice.
+            ev_.eval(spec_.behavior, flat, (uint32_t)todo.size(), trials, granularity_, w1_, w2_, ms, orient, 0,
+                     low_acceptance_ ? (uint32_t)SOPS_F_FORCE_CTA : 0u, out);
+            uint64_t cnt[6];
+            ev_.counters(cnt);
+            if (cnt[0] > 0) low_acceptance_ = (double)cnt[2] / (double)cnt[0] < 0.01;
             evaluated_ += todo.size() * T;
             for (size_t k = 0; k < todo.size(); ++k) {
                 double tot = 0.0;
@@ -281,6 +287,7 @@ private:
     uint32_t random_seed_;
     uint32_t max_div_ = 1;
     bool lower_hit_ = false;
+    bool low_acceptance_ = false;                  // last generation's accepted fraction < 1 %
     HostRng rng_;
     std::string out_dir_;
     FILE* log_;

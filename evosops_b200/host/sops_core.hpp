@@ -39,7 +39,8 @@ public:
                       std::vector<sops_result>& out) = 0;
     // final lattice (reference cell codes) + particles of instance q of the last eval() run with SOPS_F_DUMP
     virtual void dump(uint32_t instance, std::vector<uint8_t>& grid, std::vector<uint8_t>& particles, uint32_t G, uint32_t n) = 0;
-    virtual double last_device_ms() const { return 0.0; }
+    // attempts / possible / committed / launches / h2d bytes / d2h bytes of the last eval() (zeros if unknown)
+    virtual void counters(uint64_t out[6]) { for (int k = 0; k < 6; ++k) out[k] = 0; }
 };
 
 class CudaEvaluator : public Evaluator {
@@ -62,6 +63,7 @@ public:
                                  orient.empty() ? nullptr : orient.data(), steps_override, flags, out.data());
         if (rc) throw std::runtime_error(std::string("sops_eval_batch: ") + sops_last_error(ctx_));
     }
+    void counters(uint64_t out[6]) override { if (sops_batch_counters(ctx_, out)) for (int k = 0; k < 6; ++k) out[k] = 0; }
     void dump(uint32_t instance, std::vector<uint8_t>& grid, std::vector<uint8_t>& particles, uint32_t G, uint32_t n) override {
         grid.assign((size_t)G * G, 0);
         particles.assign((size_t)n * 3, 0);

@@ -63,7 +63,10 @@ typedef struct { uint32_t i0, i1, i2; float f; double norm; } sops_result;
 enum {
     SOPS_F_DUMP = 1,        /* keep final lattices + particle lists for sops_dump_state            */
     SOPS_F_INIT_ONLY = 2,   /* run 0 chain steps (init_sops_env + evaluate_fitness only)           */
-    SOPS_F_THEORY_TABLE = 4 /* use theory_gene_probability() (mod.rs:91-93, separation.rs:82-84)   */
+    SOPS_F_THEORY_TABLE = 4,/* use theory_gene_probability() (mod.rs:91-93, separation.rs:82-84)   */
+    /* Kernel choice (results are bit-identical either way; default: one warp per chain) */
+    SOPS_F_FORCE_WARP = 8,  /* one warp per chain (the default, spelled out)                        */
+    SOPS_F_FORCE_CTA = 16   /* one 4-warp CTA per chain (fast mode): pays for few, low-acceptance chains */
 };
 
 /* Create a context over n_dev CUDA devices (device_ids NULL -> devices 0..n_dev-1). */

@@ -12,6 +12,17 @@ pytestmark = pytest.mark.gpu
 W = {E.AGG: (0.0, 0.0), E.SEP: (0.65, 0.35), E.COAT: (0.65, 0.35), E.LOCO: (0.75, 0.25)}
 
 
+@pytest.fixture(params=[0, E.F_FORCE_CTA], ids=["warp", "cta"])
+def kflag(request):
+    """Kernel choice: warp per chain (default) or the opt-in 4-warp CTA per chain.  Both must give the oracle's bits."""
+    return request.param
+
+
+def _skip_redundant(rng_mode, kflag):
+    if rng_mode == E.RNG_VERIFY and kflag != 0:
+        pytest.skip("verification mode always runs the warp-per-chain kernel")
+
+
 def run_pair(ctx, beh, gs, sizes, seeds, rng_mode, steps=0, move_seeds=None, orient=None, flags=0):
     w1, w2 = W[beh]
     got = ctx.eval_batch(beh, gs, sizes, seeds, w1=w1, w2=w2, rng_mode=rng_mode, move_seeds=move_seeds,
@@ -80,69 +91,76 @@ def test_init_reproduces_reference_snapshots(ctx, fixtures, genomes):
 
 
 @pytest.mark.parametrize("rng_mode", [E.RNG_VERIFY, E.RNG_FAST])
-def test_agg_full_chains_bit_exact(ctx, genomes, rng_mode):
+def test_agg_full_chains_bit_exact(ctx, genomes, rng_mode, kflag):
+    _skip_redundant(rng_mode, kflag)
     gs = np.stack([genomes["agg_theory"].clip(0, 5), genomes["agg_evolved"], genomes["agg_random"]])
     sizes = [(6, 3)] * 4 + [(10, 7)] * 2 + [(13, 9)]
     seeds = [1, 2, 3, 4, 1, 2, 1]
-    got, want, cnt = run_pair(ctx, E.AGG, gs, sizes, seeds, rng_mode)
-    check_equal(ctx, E.AGG, gs, sizes, seeds, got, want, cnt, rng_mode, 0)
+    got, want, cnt = run_pair(ctx, E.AGG, gs, sizes, seeds, rng_mode, flags=kflag)
+    check_equal(ctx, E.AGG, gs, sizes, seeds, got, want, cnt, rng_mode, 0, flags=kflag)
 
 
 @pytest.mark.parametrize("rng_mode", [E.RNG_VERIFY, E.RNG_FAST])
-def test_agg_theory_table(ctx, genomes, rng_mode):
+def test_agg_theory_table(ctx, genomes, rng_mode, kflag):
+    _skip_redundant(rng_mode, kflag)
     gs = genomes["agg_theory"]
     sizes, seeds = [(6, 3), (10, 7), (13, 9)], [1, 1, 62813]
-    got, want, cnt = run_pair(ctx, E.AGG, gs, sizes, seeds, rng_mode, flags=E.F_THEORY_TABLE)
-    check_equal(ctx, E.AGG, gs, sizes, seeds, got, want, cnt, rng_mode, 0, flags=E.F_THEORY_TABLE)
+    got, want, cnt = run_pair(ctx, E.AGG, gs, sizes, seeds, rng_mode, flags=E.F_THEORY_TABLE | kflag)
+    check_equal(ctx, E.AGG, gs, sizes, seeds, got, want, cnt, rng_mode, 0, flags=E.F_THEORY_TABLE | kflag)
 
 
 @pytest.mark.parametrize("rng_mode", [E.RNG_VERIFY, E.RNG_FAST])
-def test_agg_many_seeds_short_chains(ctx, genomes, rng_mode):
+def test_agg_many_seeds_short_chains(ctx, genomes, rng_mode, kflag):
+    _skip_redundant(rng_mode, kflag)
     # 32 move seeds per size incl. the two-word-row class (20,14) and (26,18); chains capped at 3e5 steps
     gs = np.stack([genomes["agg_evolved"], genomes["agg_random"]])
     sizes = [(6, 3)] * 8 + [(13, 9)] * 8 + [(20, 14)] * 8 + [(26, 18)] * 8
     seeds = list(range(1, 33))
     ms = (np.arange(2 * 32, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(12345))
-    got, want, cnt = run_pair(ctx, E.AGG, gs, sizes, seeds, rng_mode, steps=300000, move_seeds=ms)
-    check_equal(ctx, E.AGG, gs, sizes, seeds, got, want, cnt, rng_mode, 300000, move_seeds=ms, dump_every=3)
+    got, want, cnt = run_pair(ctx, E.AGG, gs, sizes, seeds, rng_mode, steps=300000, move_seeds=ms, flags=kflag)
+    check_equal(ctx, E.AGG, gs, sizes, seeds, got, want, cnt, rng_mode, 300000, move_seeds=ms, dump_every=3, flags=kflag)
 
 
 @pytest.mark.parametrize("rng_mode", [E.RNG_VERIFY, E.RNG_FAST])
-def test_sep_chains_bit_exact(ctx, genomes, rng_mode):
+def test_sep_chains_bit_exact(ctx, genomes, rng_mode, kflag):
+    _skip_redundant(rng_mode, kflag)
     gs = np.stack([genomes["sep_evolved"], genomes["sep_random"]])
     sizes = [(6, 3), (6, 3), (10, 7), (13, 9), (20, 14)]
     seeds = [1, 2, 3, 71729, 5]
-    got, want, cnt = run_pair(ctx, E.SEP, gs, sizes, seeds, rng_mode, steps=400000)
-    check_equal(ctx, E.SEP, gs, sizes, seeds, got, want, cnt, rng_mode, 400000)
+    got, want, cnt = run_pair(ctx, E.SEP, gs, sizes, seeds, rng_mode, steps=400000, flags=kflag)
+    check_equal(ctx, E.SEP, gs, sizes, seeds, got, want, cnt, rng_mode, 400000, flags=kflag)
 
 
 @pytest.mark.parametrize("rng_mode", [E.RNG_VERIFY, E.RNG_FAST])
-def test_sep_theory_table_full_small_chain(ctx, genomes, rng_mode):
+def test_sep_theory_table_full_small_chain(ctx, genomes, rng_mode, kflag):
+    _skip_redundant(rng_mode, kflag)
     gs = genomes["sep_theory"]
     sizes, seeds = [(6, 3), (6, 3)], [1, 2]
-    got, want, cnt = run_pair(ctx, E.SEP, gs, sizes, seeds, rng_mode, flags=E.F_THEORY_TABLE)
-    check_equal(ctx, E.SEP, gs, sizes, seeds, got, want, cnt, rng_mode, 0, flags=E.F_THEORY_TABLE)
+    got, want, cnt = run_pair(ctx, E.SEP, gs, sizes, seeds, rng_mode, flags=E.F_THEORY_TABLE | kflag)
+    check_equal(ctx, E.SEP, gs, sizes, seeds, got, want, cnt, rng_mode, 0, flags=E.F_THEORY_TABLE | kflag)
 
 
 @pytest.mark.parametrize("rng_mode", [E.RNG_VERIFY, E.RNG_FAST])
-def test_coat_chains_bit_exact(ctx, genomes, rng_mode):
+def test_coat_chains_bit_exact(ctx, genomes, rng_mode, kflag):
+    _skip_redundant(rng_mode, kflag)
     rng = np.random.default_rng(7)
     gs = np.stack([genomes["coat_random"], rng.integers(0, 4, size=600, dtype=np.uint8)])
     sizes = [(20, 5, 2), (20, 5, 2), (26, 8, 4), (12, 2, 1)]
     seeds = [1, 2, 3, 4]
-    got, want, cnt = run_pair(ctx, E.COAT, gs, sizes, seeds, rng_mode, steps=400000)
-    check_equal(ctx, E.COAT, gs, sizes, seeds, got, want, cnt, rng_mode, 400000)
+    got, want, cnt = run_pair(ctx, E.COAT, gs, sizes, seeds, rng_mode, steps=400000, flags=kflag)
+    check_equal(ctx, E.COAT, gs, sizes, seeds, got, want, cnt, rng_mode, 400000, flags=kflag)
 
 
 @pytest.mark.parametrize("rng_mode", [E.RNG_VERIFY, E.RNG_FAST])
-def test_loco_chains_bit_exact(ctx, genomes, rng_mode):
+def test_loco_chains_bit_exact(ctx, genomes, rng_mode, kflag):
+    _skip_redundant(rng_mode, kflag)
     rng = np.random.default_rng(11)
     gs = np.stack([genomes["loco_random"], rng.integers(0, 3, size=144, dtype=np.uint8)])
     sizes = [(6, 3), (10, 7), (13, 9), (13, 9), (20, 14), (26, 18)]
     seeds = [1, 2, 3, 4, 5, 6]
     orient = np.asarray([[1, 2, 3, 1, 2, 3], [3, 1, 2, 2, 3, 1]], dtype=np.uint8)
-    got, want, cnt = run_pair(ctx, E.LOCO, gs, sizes, seeds, rng_mode, steps=400000, orient=orient)
-    check_equal(ctx, E.LOCO, gs, sizes, seeds, got, want, cnt, rng_mode, 400000, orient=orient)
+    got, want, cnt = run_pair(ctx, E.LOCO, gs, sizes, seeds, rng_mode, steps=400000, orient=orient, flags=kflag)
+    check_equal(ctx, E.LOCO, gs, sizes, seeds, got, want, cnt, rng_mode, 400000, orient=orient, flags=kflag)
 
 
 def test_errors_not_panics(ctx, genomes):
