@@ -234,3 +234,41 @@ def test_results_identical_across_device_counts(genomes):
     finally:
         one.close()
         two.close()
+
+
+@pytest.mark.parametrize("rng_mode", [E.RNG_VERIFY, E.RNG_FAST])
+def test_ragged_step_counts(ctx, genomes, rng_mode, kflag):
+    # chains shorter than, equal to and just past one 32-step batch (and one 128-step super-batch)
+    _skip_redundant(rng_mode, kflag)
+    gs = np.stack([genomes["agg_random"], genomes["agg_evolved"]])
+    for steps in (1, 5, 31, 32, 33, 64, 127, 128, 129, 1000):
+        got, want, cnt = run_pair(ctx, E.AGG, gs, [(6, 3), (10, 7)], [3, 4], rng_mode, steps=steps, flags=kflag)
+        check_equal(ctx, E.AGG, gs, [(6, 3), (10, 7)], [3, 4], got, want, cnt, rng_mode, steps, flags=kflag)
+
+
+@pytest.mark.parametrize("beh", [E.AGG, E.SEP, E.COAT, E.LOCO])
+def test_largest_supported_arena(ctx, genomes, beh, kflag):
+    # arena_layers 29 is the widest lattice the 64-bit rows hold (G + 4 = 63); one size above is refused
+    name = {E.AGG: "agg_random", E.SEP: "sep_random", E.COAT: "coat_random", E.LOCO: "loco_random"}[beh]
+    size = (29, 8, 4) if beh == E.COAT else (29, 20)
+    orient = np.asarray([[3]], dtype=np.uint8) if beh == E.LOCO else None
+    for rng_mode in (E.RNG_VERIFY, E.RNG_FAST):
+        if rng_mode == E.RNG_VERIFY and kflag:
+            continue
+        got, want, cnt = run_pair(ctx, beh, genomes[name], [size], [7], rng_mode, steps=200000, orient=orient, flags=kflag)
+        check_equal(ctx, beh, genomes[name], [size], [7], got, want, cnt, rng_mode, 200000, orient=orient, flags=kflag)
+    with pytest.raises(E.SopsError) as ei:
+        ctx.eval_batch(beh, genomes[name], [(30,) + size[1:]], [7])
+    assert ei.value.code == -4
+
+
+def test_empty_and_null_batches_are_errors(ctx, genomes):
+    with pytest.raises(E.SopsError) as ei:
+        ctx.eval_batch(E.AGG, genomes["agg_random"], [], [])
+    assert ei.value.code == -1
+    with pytest.raises(E.SopsError) as ei:
+        ctx.eval_batch(E.AGG, np.zeros((0, 48), dtype=np.uint8), [(6, 3)], [1])
+    assert ei.value.code == -1
+    with pytest.raises(E.SopsError) as ei:
+        ctx.eval_batch(E.LOCO, genomes["loco_random"], [(6, 3)], [1], orient=np.asarray([[4]], dtype=np.uint8))
+    assert ei.value.code == -1
