@@ -105,8 +105,9 @@ __device__ __forceinline__ uint32_t wy_mod_1000(uint32_t r32, uint64_t move_seed
 __device__ __forceinline__ void philox2x32_10(uint32_t c0, uint32_t c1, uint32_t key, uint32_t& o0, uint32_t& o1) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        uint64_t p = (uint64_t)0xD256D193u * c0;
-        uint32_t hi = (uint32_t)(p >> 32), lo = (uint32_t)p;
+        uint64_t p;
+        asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(c0), "r"(0xD256D193u));   // one IMAD.WIDE: hi and lo together
+        const uint32_t hi = (uint32_t)(p >> 32), lo = (uint32_t)p;
         c0 = hi ^ key ^ c1;
         c1 = lo;
         key += 0x9E3779B9u;
