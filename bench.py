@@ -287,13 +287,16 @@ def main():
         n_sweep, cap = 50000, 200000
         seeds = list(range(1 + rank * n_sweep, 1 + (rank + 1) * n_sweep))
         for nm, md in (("fast", E.RNG_FAST), ("verify", E.RNG_VERIFY)):
-            ctx.prepare(E.AGG, gs[:1], [(13, 9)] * n_sweep, seeds, gran=args.gran, rng_mode=md, steps_override=cap)
+            # one fixed genome (the reference's evolved aggregation genome) x many seeds
+            ctx.prepare(E.AGG, np.asarray(EVOLVED_AGG, dtype=np.uint8).reshape(1, 48), [(13, 9)] * n_sweep, seeds, gran=args.gran,
+                        rng_mode=md, steps_override=cap)
             ctx.launch(); ctx.sync()
             ctx.launch(); ms_s = ctx.sync()
             ctx.collect()
             tot = reduce(float(n_sweep) * cap, dist.ReduceOp.SUM if world > 1 else None)
             extra["sweep_13_9_%s" % nm] = {"value": tot / (reduce(ms_s, dist.ReduceOp.MAX if world > 1 else None) * 1e-3),
-                                           "unit": "attempts/s", "instances_per_gpu": n_sweep, "steps_cap": cap}
+                                           "unit": "attempts/s", "instances_per_gpu": n_sweep, "steps_cap": cap,
+                                           "genome": "reference evolved agg genome"}
 
     if rank == 0:
         peaks, peak_src = measured_peaks()

@@ -695,8 +695,11 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
     __syncwarp();
 }
 
+#ifndef SOPS_MIN_BLOCKS
+#define SOPS_MIN_BLOCKS 1
+#endif
 template <int BEH, int RW, int MODE>
-__global__ void __launch_bounds__(256) sops_chain_kernel(const KParams P) {
+__global__ void __launch_bounds__(256, SOPS_MIN_BLOCKS) sops_chain_kernel(const KParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint4 s_dirtab[8];
     if (threadIdx.x == 0) {
