@@ -108,8 +108,8 @@ struct Group {                      // one kernel launch: instances of one row-w
 
 struct Dev {
     int id = 0, n_sm = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: the second row-width class of a mixed batch runs concurrently
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     // device buffers (grown on demand)
     Instance* d_inst = nullptr; size_t cap_inst = 0;
     uint8_t* d_genomes = nullptr; size_t cap_genomes = 0;
@@ -247,6 +247,9 @@ int sops_ctx_create(sops_ctx** out, const int* device_ids, int n_dev) {
         if (d.id < 0 || d.id >= have) { delete ctx; return SOPS_E_ARG; }
         cudaError_t e = cudaSetDevice(d.id);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream2, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_join, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreate(&d.ev0);
         if (e == cudaSuccess) e = cudaEventCreate(&d.ev1);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&d.n_sm, cudaDevAttrMultiProcessorCount, d.id);
@@ -268,6 +271,9 @@ void sops_ctx_destroy(sops_ctx* ctx) {
         cudaFreeHost(d.h_inst); cudaFreeHost(d.h_out); cudaFreeHost(d.h_counters); cudaFreeHost(d.h_dump);
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
+        if (d.ev_fork) cudaEventDestroy(d.ev_fork);
+        if (d.ev_join) cudaEventDestroy(d.ev_join);
+        if (d.stream2) cudaStreamDestroy(d.stream2);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     cudaFreeHost(ctx->h_genomes);
@@ -511,6 +517,10 @@ int sops_batch_launch(sops_ctx* ctx) {
         CK(cudaSetDevice(d.id));
         CK(cudaMemsetAsync(d.d_counters, 0, 8 * sizeof(unsigned long long), d.stream));
         CK(cudaEventRecord(d.ev0, d.stream));
+        if (d.groups.size() > 1) {                           // fork point: after the counter reset, before any chain kernel
+            CK(cudaEventRecord(d.ev_fork, d.stream));
+            CK(cudaStreamWaitEvent(d.stream2, d.ev_fork, 0));
+        }
         for (size_t gi = 0; gi < d.groups.size(); ++gi) {
             const Group& g = d.groups[gi];
             KParams kp;
@@ -532,8 +542,14 @@ int sops_batch_launch(sops_ctx* ctx) {
             kp.off_pos = g.off_pos; kp.off_thr = g.off_thr; kp.off_aux = g.off_aux;
             kp.plane_words = g.plane_words; kp.pos_words = g.pos_words;
             kernel_fn fn = g.cta_w ? kernel_for_cta(ctx->behavior, g.rw) : kernel_for(ctx->behavior, g.rw, ctx->rng_mode);
-            fn<<<g.blocks, g.wpb * 32, g.smem, d.stream>>>(kp);
+            cudaStream_t st = d.stream;
+            if (gi > 0) st = d.stream2;                      // independent chains: the two classes run concurrently
+            fn<<<g.blocks, g.wpb * 32, g.smem, st>>>(kp);
             CK(cudaGetLastError());
+            if (gi > 0) {
+                CK(cudaEventRecord(d.ev_join, st));
+                CK(cudaStreamWaitEvent(d.stream, d.ev_join, 0));
+            }
             ++ctx->launches;
         }
         CK(cudaEventRecord(d.ev1, d.stream));
