@@ -182,7 +182,7 @@ int main(int argc, char** argv) {
             std::fprintf(log, "\nStarting %s GA Experiment...\n\n", titles[args.behavior]);
             GeneticAlgo ga(ev, args.behavior, args.population, args.max_generations, args.elitist_count, args.mutation_rate,
                            args.granularity, true, sizes, args.seeds, w1, w2, random_trial_seed,
-                           args.have_ga_seed ? args.ga_seed : now_ns, args.out_dir, log);
+                           args.have_ga_seed ? args.ga_seed : now_ns, args.out_dir, log, args.verbose);
             ga.run_through();
         } else {
             std::fprintf(log, "Snapshots: %s\n", args.snaps ? "true" : "false");

@@ -84,10 +84,10 @@ public:
     // init_ga: base_ga.rs:72-116 (random genes in 0..=granularity)
     GeneticAlgo(Evaluator& ev, int behavior, uint16_t population_size, uint16_t max_gen, uint16_t elitist_cnt, double mut_rate,
                 uint8_t granularity, bool perform_cross, std::vector<sops_size> sizes, std::vector<uint64_t> trial_seeds,
-                float w1, float w2, uint32_t random_seed, uint64_t ga_seed, const std::string& out_dir, FILE* log)
+                float w1, float w2, uint32_t random_seed, uint64_t ga_seed, const std::string& out_dir, FILE* log, bool verbose = false)
         : ev_(ev), spec_(spec_for(behavior)), max_gen_(max_gen), elitist_cnt_(elitist_cnt), mut_rate_(mut_rate), granularity_(granularity),
           perform_cross_(perform_cross), sizes_(std::move(sizes)), trial_seeds_(std::move(trial_seeds)), w1_(w1), w2_(w2),
-          random_seed_(random_seed), rng_(ga_seed), out_dir_(out_dir), log_(log) {
+          random_seed_(random_seed), rng_(ga_seed), out_dir_(out_dir), log_(log), verbose_(verbose) {
         L_ = genome_len(behavior);
         if (spec_.weights_fmt) {
             std::fprintf(log_, spec_.weights_fmt, fmt_display(w1).c_str(), fmt_display(w2).c_str());
@@ -252,6 +252,10 @@ public:
             }
             const auto secs = std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - t0).count();
             std::fprintf(log_, "Generation Elapsed Time: %llds\n", (long long)secs);
+            if (verbose_)                                                          // extension (-v): the reference only has whole seconds
+                std::fprintf(log_, "Generation Wall Time: %.3fs  Evaluated Instances: %llu  Kernel: %s\n",
+                             std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(),
+                             (unsigned long long)evaluated_, low_acceptance_ ? "cta" : "warp");
             std::fflush(log_);
         }
     }
@@ -291,6 +295,7 @@ private:
     HostRng rng_;
     std::string out_dir_;
     FILE* log_;
+    bool verbose_ = false;
     std::vector<GenomeRec> population_;
     std::unordered_map<std::string, double> cache_;
     uint64_t evaluated_ = 0;
