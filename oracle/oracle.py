@@ -60,6 +60,7 @@ def lib():
         L.oracle_eval_batch.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                         C.c_uint32, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.oracle_lemire_redraws.restype = C.c_ulonglong
         _LIB = L
     return _LIB
 
@@ -195,3 +196,8 @@ def eval_batch(behavior, genomes, sizes, seeds, w1=0.65, w2=0.35, rng_mode=0, mo
     if rc != 0:
         raise ValueError("oracle_eval_batch rc=%d" % rc)
     return out, counters
+
+
+def lemire_redraws():
+    """How many times the oracle's WyRand Lemire loops redrew so far (process-wide test instrumentation)."""
+    return int(lib().oracle_lemire_redraws())

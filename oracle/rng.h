@@ -15,6 +15,7 @@
 //   * Philox2x32-10 (Salmon et al. 2011, Random123): the fast-mode counter RNG (ours, not the
 //       reference's); pinned by the Random123 known-answer vectors in tests.
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <cstring>
 
@@ -95,6 +96,9 @@ struct StdRng {
 };
 
 // ---------------------------------------------------------------- fastrand 1.9.0 (WyRand) -------
+// test instrumentation: how often Lemire's rejection loop actually redrew (u32 and u64 paths)
+static std::atomic<unsigned long long> g_lemire_redraws{0};
+
 struct WyRand {
     uint64_t s;
     explicit WyRand(uint64_t seed) : s(seed) {}
@@ -111,6 +115,7 @@ struct WyRand {
         if (lo < n) {
             uint64_t t = (0 - n) % n;
             while (lo < t) {
+                g_lemire_redraws.fetch_add(1, std::memory_order_relaxed);
                 r = gen_u64();
                 m = (unsigned __int128)r * n;
                 hi = (uint64_t)(m >> 64); lo = (uint64_t)m;
@@ -125,6 +130,7 @@ struct WyRand {
         if (lo < n) {
             uint32_t t = (0u - n) % n;
             while (lo < t) {
+                g_lemire_redraws.fetch_add(1, std::memory_order_relaxed);
                 r = gen_u32();
                 m = (uint64_t)r * n;
                 hi = (uint32_t)(m >> 32); lo = (uint32_t)m;

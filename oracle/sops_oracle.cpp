@@ -649,6 +649,8 @@ int oracle_eval_batch(int behavior, const uint8_t* genomes, uint32_t P, uint32_t
     return rc_all;
 }
 
+unsigned long long oracle_lemire_redraws() { return oracle::g_lemire_redraws.load(); }
+
 int oracle_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
 
 }  // extern "C"

@@ -272,3 +272,17 @@ def test_empty_and_null_batches_are_errors(ctx, genomes):
     with pytest.raises(E.SopsError) as ei:
         ctx.eval_batch(E.LOCO, genomes["loco_random"], [(6, 3)], [1], orient=np.asarray([[4]], dtype=np.uint8))
     assert ei.value.code == -1
+
+
+def test_verify_mode_lemire_rejection_redraws_are_reproduced(ctx, genomes):
+    # fastrand's u16(1..=1000) redraws with p = 296 / 2^32 per probability draw; every later draw of the
+    # chain shifts when it happens.  96 full (10,7) chains make ~2e8 probability draws -> a dozen redraws.
+    gs = np.stack([genomes["agg_random"], genomes["agg_evolved"], genomes["agg_theory"].clip(0, 5)])
+    sizes, seeds = [(10, 7)] * 32, list(range(101, 133))
+    before = O.lemire_redraws()
+    want, cnt = O.eval_batch(O.AGG, gs, sizes, seeds, rng_mode=0)
+    assert O.lemire_redraws() - before >= 3, "workload too small to exercise the rejection loop"
+    got = ctx.eval_batch(E.AGG, gs, sizes, seeds, rng_mode=E.RNG_VERIFY)
+    assert np.array_equal(got["i0"], want["i0"])
+    c = ctx.counters()
+    assert (c["attempts"], c["possible"], c["committed"]) == tuple(int(v) for v in cnt)
