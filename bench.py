@@ -141,6 +141,16 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def issue_view(attempts_per_s, p_poss, sm_mhz):
+    """SURVEY.md 8d's binding ceiling: SM issue.  ALG_INT_OPS/attempt = 50 + 90 p_poss thread-instructions,
+    peak = 148 SMs x 4 warp-instructions/clk x 32 lanes x clock."""
+    peak = 148 * 4 * 32 * sm_mhz * 1e6
+    ops = 50.0 + 90.0 * p_poss
+    ceiling = peak / ops
+    return {"alg_thread_inst_per_attempt": ops, "peak_thread_inst_per_s": peak, "ceiling_attempts_per_s": ceiling,
+            "frac": attempts_per_s / ceiling}
+
+
 def attempts_per_generation():
     tot = 0
     for (a, p) in SIZES_C2:
@@ -253,6 +263,7 @@ def main():
     mean_fitness = float(res["norm"].mean())
 
     extra = {}
+    sweep_local = None
     if not args.no_extra:
         # the other RNG mode on the same batch, and a throughput-bound sweep (config 5 style, capped chains)
         other = E.RNG_VERIFY if mode == E.RNG_FAST else E.RNG_FAST
@@ -293,6 +304,9 @@ def main():
             ctx.launch(); ctx.sync()
             ctx.launch(); ms_s = ctx.sync()
             ctx.collect()
+            cs = ctx.counters()
+            if nm == "fast":
+                sweep_local = (ms_s, cs["possible"] / cs["attempts"], cs["committed"] / cs["attempts"], float(cs["attempts"]))
             tot = reduce(float(n_sweep) * cap, dist.ReduceOp.SUM if world > 1 else None)
             extra["sweep_13_9_%s" % nm] = {"value": tot / (reduce(ms_s, dist.ReduceOp.MAX if world > 1 else None) * 1e-3),
                                            "unit": "attempts/s", "instances_per_gpu": n_sweep, "steps_cap": cap,
@@ -325,8 +339,17 @@ def main():
                              "kernel": "sops_chain_kernel<AGG,RW=1,%s>" % args.rng, "kernel_ms": k_ms,
                              "alg_bytes_per_attempt": alg_bytes, "p_poss": p_poss, "p_acc": p_acc,
                              "peak_source": "%s sm_max_mhz x 148 SMs x 128 B/clk shared memory" % peak_src,
-                             "note": "chains are dependent-latency bound at 750 warps/GPU; see DESIGN.md"},
+                             "issue": issue_view(attempts_step / (k_ms * 1e-3), p_poss, sm_mhz),
+                             "note": "750 chains on 9472 warp slots: dependent-latency bound, the slowest genome's chains set the time; see DESIGN.md"},
                 "mean_fitness": mean_fitness}
+        if sweep_local:
+            ms_s, pp_s, pa_s, att_s = sweep_local
+            ab = 10.0 + 22.3 * pp_s + 18.0 * pa_s
+            ach = ab * att_s / (ms_s * 1e-3) / 1e9
+            extra["roofline_sweep"] = {"bound": "smem", "achieved": ach, "peak": peak_smem, "unit": "GB/s", "frac": ach / peak_smem,
+                                       "traffic": None, "kernel": "sops_chain_kernel<AGG,RW=1,fast> on the 50000-chain sweep (rank 0)",
+                                       "kernel_ms": ms_s, "alg_bytes_per_attempt": ab, "p_poss": pp_s, "p_acc": pa_s,
+                                       "issue": issue_view(att_s / (ms_s * 1e-3), pp_s, sm_mhz)}
         line.update(extra)
         if world == 1:
             import multiprocessing
