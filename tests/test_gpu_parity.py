@@ -286,3 +286,69 @@ def test_verify_mode_lemire_rejection_redraws_are_reproduced(ctx, genomes):
     assert np.array_equal(got["i0"], want["i0"])
     c = ctx.counters()
     assert (c["attempts"], c["possible"], c["committed"]) == tuple(int(v) for v in cnt)
+
+
+# ---------------------------------------------------------------- full-size properties ------------------
+DIRS6 = [(-1, 0), (1, 0), (0, -1), (0, 1), (-1, -1), (1, 1)]
+
+
+def _neighbour_sums(grid, cells_mask, nbr_mask_fn):
+    """sum over cells in cells_mask of #neighbours satisfying nbr_mask_fn (reference get_neighbors_cnt)."""
+    G = grid.shape[0]
+    pad = np.zeros((G + 2, G + 2), dtype=grid.dtype)
+    pad[1:-1, 1:-1] = grid
+    tot = 0
+    for di, dj in DIRS6:
+        shifted = pad[1 + di:1 + di + G, 1 + dj:1 + dj + G]
+        tot += int((cells_mask & nbr_mask_fn(shifted, grid)).sum())
+    return tot
+
+
+def test_full_size_c2_generation_properties(ctx):
+    # BASELINE config C2 at full size (750 chains, 6.24e9 attempts): too big for the oracle, so checked through
+    # size-independent properties: determinism, kernel-variant invariance, particle conservation, particle list
+    # <-> lattice consistency, and the fitness integer recomputed on the host from the dumped lattice
+    import bench
+    gs = bench.synthetic_genomes(0, bench.POP_C2, 48)
+    tsz, tsd = bench.trial_list(bench.SIZES_C2, bench.SEEDS_C2)
+    a = ctx.eval_batch(E.AGG, gs, tsz, tsd, rng_mode=E.RNG_FAST, flags=E.F_DUMP)
+    c = ctx.counters()
+    assert c["attempts"] == sum(50 * (3 * p * (p + 1) + 1) ** 3 * 5 for _, p in bench.SIZES_C2)
+    T = len(tsz)
+    for q in range(0, bench.POP_C2 * T, 7):
+        G, n, _ = E.instance_shape(E.AGG, tsz[q % T])
+        grid, parts = ctx.dump_state(q, G, n)
+        assert int((grid == 1).sum()) == n
+        assert len({(int(x), int(y)) for x, y, _ in parts}) == n and all(grid[x, y] == 1 for x, y, _ in parts)
+        arena = tsz[q % T][0]
+        ii, jj = np.indices(grid.shape)
+        assert np.array_equal(grid == 2, np.abs(ii - jj) > arena)           # boundary mask untouched
+        edges = _neighbour_sums(grid, grid == 1, lambda nb, g: nb == 1) // 2
+        assert edges == a.reshape(-1)[q]["i0"]
+    b = ctx.eval_batch(E.AGG, gs, tsz, tsd, rng_mode=E.RNG_FAST)             # determinism
+    assert np.array_equal(a, b)
+    d = ctx.eval_batch(E.AGG, gs[:10], tsz, tsd, rng_mode=E.RNG_FAST, flags=E.F_FORCE_CTA)   # kernel-variant and batch invariance
+    assert np.array_equal(a[:10], d)
+
+
+def test_full_size_sep_generation_properties(ctx, genomes):
+    # config C3's chain shape (sep (13,9), full n^3 = 1.97e7 steps), 16 genomes x 5 seeds
+    rng = np.random.default_rng(21)
+    gs = np.concatenate([genomes["sep_evolved"][None], rng.integers(0, 11, size=(15, 600), dtype=np.uint8)])
+    sizes, seeds = [(13, 9)] * 5, [1, 2, 3, 4, 5]
+    a = ctx.eval_batch(E.SEP, gs, sizes, seeds, w1=0.65, w2=0.35, rng_mode=E.RNG_FAST, flags=E.F_DUMP)
+    for q in range(0, 80, 3):
+        grid, parts = ctx.dump_state(q, 27, 270)
+        assert [int((grid == c).sum()) for c in (1, 2, 3)] == [90, 90, 90]
+        assert all(grid[x, y] == s for x, y, s in parts) and [int(s) for s in parts[:, 2]] == [1] * 90 + [2] * 90 + [3] * 90
+        occ = (grid >= 1) & (grid <= 3)
+        Esum = _neighbour_sums(grid, occ, lambda nb, g: (nb >= 1) & (nb <= 3))
+        Ssum = _neighbour_sums(grid, occ, lambda nb, g: nb == g)
+        r = a.reshape(-1)[q]
+        assert (Esum, Ssum) == (r["i0"], r["i1"])
+        f = np.float32(0.65) * ((np.float32(Esum) / np.float32(2)) / np.float32(3 * (3 * 81 + 9 - 1))) + \
+            np.float32(0.35) * ((np.float32(Ssum) / np.float32(6)) / np.float32(3 * 81 - 9 - 1))
+        assert abs(float(f) - float(r["f"])) <= 1e-6 * float(f)
+    assert a[0]["norm"].mean() > 0.9                                          # the reference's evolved genome separates (0.95-0.98)
+    b = ctx.eval_batch(E.SEP, gs, sizes, seeds, w1=0.65, w2=0.35, rng_mode=E.RNG_FAST)
+    assert np.array_equal(a, b)
