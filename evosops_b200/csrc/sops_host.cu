@@ -191,8 +191,12 @@ typedef void (*kernel_fn)(const KParams);
 template <int BEH>
 kernel_fn pick_kernel(int rw, int mode) {
     if (rw == 1) return mode == 0 ? sops::sops_chain_kernel<BEH, 1, 0> : sops::sops_chain_kernel<BEH, 1, 1>;
-    return mode == 0 ? sops::sops_chain_kernel<BEH, 2, 0> : sops::sops_chain_kernel<BEH, 2, 1>;
+    if (rw == 2) return mode == 0 ? sops::sops_chain_kernel<BEH, 2, 0> : sops::sops_chain_kernel<BEH, 2, 1>;
+    if (rw == 4) return mode == 0 ? sops::sops_chain_kernel<BEH, 4, 0> : sops::sops_chain_kernel<BEH, 4, 1>;
+    return mode == 0 ? sops::sops_chain_kernel<BEH, 8, 0> : sops::sops_chain_kernel<BEH, 8, 1>;
 }
+// row width class of a padded grid side: 32-bit words per lattice row
+int rw_of(uint32_t pg) { return pg <= 32 ? 1 : pg <= 64 ? 2 : pg <= 128 ? 4 : 8; }
 // CTA-per-chain variant: 4 warps per chain (opt-in, SOPS_F_FORCE_CTA; see DESIGN.md for when it pays)
 kernel_fn kernel_for_cta(int beh, int rw) {
     switch (beh) {
@@ -223,7 +227,7 @@ void layout_group(Group& g, int beh, uint32_t max_pg, uint32_t max_n) {
     g.off_p2 = off; if (three) off += g.plane_words;
     g.off_pos = off; off += g.pos_words;
     g.off_thr = off; off += thr_words;
-    g.off_aux = off; if (beh == SOPS_LOCO) off += SOPS_LIGHT_WORDS;
+    g.off_aux = off; if (beh == SOPS_LOCO) off += SOPS_LOCO_AUX_WORDS;
     off = (off + 1u) & ~1u;
     off |= 2u;                                                  // stride = 2 mod 4 words: spreads warps over banks, keeps 8-byte alignment
     g.words_per_warp = off;
@@ -333,7 +337,9 @@ int sops_batch_prepare(sops_ctx* ctx, int behavior, const uint8_t* genomes, uint
     for (uint32_t t = 0; t < T; ++t) {
         int rc = shape_of(behavior, trial_sizes[t], &shp[t]);
         if (rc) return fail(ctx, rc, "invalid size tuple at trial " + std::to_string(t));
-        if (shp[t].G + 4 > 64) return fail(ctx, SOPS_E_UNSUPPORTED, "arena_layers > 29 not implemented by the kernels");
+        if (shp[t].G + 4 > 255) return fail(ctx, SOPS_E_UNSUPPORTED, "arena_layers > 125 not implemented by the kernels (u8 padded coordinates)");
+        if (behavior == SOPS_LOCO && trial_sizes[t].arena > 63)
+            return fail(ctx, SOPS_E_UNSUPPORTED, "loco is defined for arena_layers <= 63 (u8 arithmetic in locomotion.rs wraps beyond)");
             }
     if (loco_orient && behavior == SOPS_LOCO)
         for (uint32_t q = 0; q < N; ++q)
@@ -417,16 +423,16 @@ int sops_batch_prepare(sops_ctx* ctx, int behavior, const uint8_t* genomes, uint
         d.groups.clear();
         if (d.n_inst == 0) continue;
         // split by row-width class (stable: keeps the cost order inside each class)
-        std::vector<uint32_t> cls[2];
-        for (uint32_t q : d.global_of) cls[(shp[q % T].G + 4 > 32) ? 1 : 0].push_back(q);
+        std::vector<uint32_t> cls[4];
+        for (uint32_t q : d.global_of) { const int rw = rw_of(shp[q % T].G + 4); cls[rw == 1 ? 0 : rw == 2 ? 1 : rw == 4 ? 2 : 3].push_back(q); }
         d.global_of.clear();
         CK(grow_host(&d.h_inst, &d.hcap_inst, (size_t)d.n_inst));
         size_t dump_words = 0;
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < 4; ++c) {
             if (cls[c].empty()) continue;
             Group grp;
             memset(&grp, 0, sizeof(grp));
-            grp.rw = c + 1;
+            grp.rw = 1 << c;
             grp.first = (uint32_t)d.global_of.size();
             grp.count = (uint32_t)cls[c].size();
             uint32_t max_pg = 0, max_n = 0;
@@ -456,7 +462,7 @@ int sops_batch_prepare(sops_ctx* ctx, int behavior, const uint8_t* genomes, uint
             // kernel choice: one warp per chain, unless the caller asks for the 4-warp CTA-per-chain variant
             // (fast mode only; it pays when few chains with very low acceptance run, i.e. late GA generations)
             const size_t smem_per_warp = (size_t)grp.words_per_warp * 4;
-            grp.cta_w = (rng_mode == SOPS_RNG_FAST && (flags & SOPS_F_FORCE_CTA) && !(flags & SOPS_F_FORCE_WARP)) ? 4 : 0;
+            grp.cta_w = (rng_mode == SOPS_RNG_FAST && (flags & SOPS_F_FORCE_CTA) && !(flags & SOPS_F_FORCE_WARP) && grp.rw <= 2) ? 4 : 0;
             int per_sm = 0;
             if (grp.cta_w) {
                 kernel_fn fn = kernel_for_cta(behavior, grp.rw);

@@ -62,7 +62,8 @@ struct KParams {
     uint32_t plane_words, pos_words;
 };
 
-#define SOPS_LIGHT_WORDS 32u        // 64 u16 beams (a <= 29 -> 2a+1 <= 59)
+#define SOPS_LIGHT_WORDS 64u        // 128 u16 beams: loco is defined for arena_layers <= 63 (u8 arithmetic upstream), 2a+1 <= 127
+#define SOPS_LOCO_AUX_WORDS (SOPS_LIGHT_WORDS + 128u)   // + one u32 per beam of init scratch
 
 // ---------------------------------------------------------------------- direction tables --------
 // Directions in the reference's order (mod.rs:80-82): (-1,0) (1,0) (0,-1) (0,1) (-1,-1) (1,1).
@@ -116,7 +117,19 @@ __device__ __forceinline__ void pred_store_u16(bool q, const uint16_t* addr, uin
 }
 
 // ------------------------------------------------------------------------------ bit planes ------
-template <int RW> struct Plane;
+// RW 32-bit words per row: 1 and 2 are specialised (PG <= 32 / 64), the generic form (4, 8) serves PG <= 128 / 256
+template <int RW> struct Plane {
+    static __device__ __forceinline__ uint32_t seg(const uint32_t* p, uint32_t r, uint32_t c0, uint32_t m) {
+        const uint32_t* row = p + RW * r;
+        const uint32_t k = c0 >> 5;
+        // a 5-bit segment never crosses the end of the row, so the clamped `hi` word is only read, never used, there
+        return __funnelshift_r(row[k], row[k + 1 < RW ? k + 1 : RW - 1], c0 & 31u) & m;
+    }
+    static __device__ __forceinline__ uint32_t bit(const uint32_t* p, uint32_t r, uint32_t c) { return (p[RW * r + (c >> 5)] >> (c & 31)) & 1u; }
+    static __device__ __forceinline__ void atom_or(uint32_t* p, uint32_t r, uint32_t c) { atomicOr(&p[RW * r + (c >> 5)], 1u << (c & 31)); }
+    static __device__ __forceinline__ void atom_xor(uint32_t* p, uint32_t r, uint32_t c) { atomicXor(&p[RW * r + (c >> 5)], 1u << (c & 31)); }
+    static __device__ __forceinline__ const uint32_t* word(const uint32_t* p, uint32_t r, uint32_t c) { return p + RW * r + (c >> 5); }
+};
 template <> struct Plane<1> {       // padded grid side <= 32: one u32 per row
     static __device__ __forceinline__ uint32_t seg(const uint32_t* p, uint32_t r, uint32_t c0, uint32_t m) { return (p[r] >> c0) & m; }
     static __device__ __forceinline__ uint32_t bit(const uint32_t* p, uint32_t r, uint32_t c) { return (p[r] >> c) & 1u; }
@@ -498,7 +511,7 @@ __device__ __forceinline__ uint32_t init_instance(const KParams& P, const Lat& L
         // light table: zig-zag initial fronts (locomotion.rs:116-168) raised to the front-most
         // particle of each beam during placement (199-225).  The sequential "replace if >=" rule is
         // order independent (a running maximum), so it is rebuilt here with shared-memory atomicMax.
-        uint32_t* tmp = reinterpret_cast<uint32_t*>(L.thr);  // thresholds are staged afterwards
+        uint32_t* tmp = reinterpret_cast<uint32_t*>(L.light) + SOPS_LIGHT_WORDS;   // init scratch behind the light table
         const uint32_t o = g.orient, nb = 2 * a + 1;
         for (uint32_t b = lane; b < nb; b += 32) {
             uint32_t x, y;
@@ -689,7 +702,7 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
         for (uint32_t w = lane; w < (g.n + 1) / 2; w += 32) dst[3 * pw + w] = pos32[w];
         if (BEH == LOCO) {
             const uint32_t* l32 = reinterpret_cast<const uint32_t*>(L.light);
-            dst[3 * pw + P.pos_words + lane] = l32[lane];
+            for (uint32_t w = lane; w < SOPS_LIGHT_WORDS; w += 32) dst[3 * pw + P.pos_words + w] = l32[w];
         }
     }
     __syncwarp();
@@ -925,7 +938,7 @@ __global__ void __launch_bounds__(32 * W) sops_chain_cta_kernel(const KParams P)
                 for (uint32_t w = lane; w < (g.n + 1) / 2; w += 32) dst[3 * pw + w] = pos32[w];
                 if (BEH == LOCO) {
                     const uint32_t* l32 = reinterpret_cast<const uint32_t*>(L.light);
-                    dst[3 * pw + P.pos_words + lane] = l32[lane];
+                    for (uint32_t w = lane; w < SOPS_LIGHT_WORDS; w += 32) dst[3 * pw + P.pos_words + w] = l32[w];
                 }
             }
         }

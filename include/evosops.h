@@ -42,7 +42,7 @@ enum {
     SOPS_E_ARG = -1,        /* null pointer / bad enum / empty batch                              */
     SOPS_E_GENE = -2,       /* gene value indexes past the probability table (reference panics)   */
     SOPS_E_SIZE = -3,       /* more particles than free cells (reference never terminates), a>127 */
-    SOPS_E_UNSUPPORTED = -4,/* size outside what the kernels implement            */
+    SOPS_E_UNSUPPORTED = -4,/* arena_layers > 125 (loco: > 63): outside the kernels' u8 coordinates   */
     SOPS_E_CUDA = -5,       /* CUDA runtime error                                                 */
     SOPS_E_STATE = -6,      /* call order (e.g. collect before launch, dump without SOPS_F_DUMP)  */
     SOPS_E_INIT_REJECT = -7 /* a placement draw hit the Uniform zone rejection (p < 2^-58)        */

@@ -173,7 +173,7 @@ def test_errors_not_panics(ctx, genomes):
         ctx.eval_batch(E.AGG, genomes["agg_evolved"], [(3, 6)], [1])
     assert ei.value.code == -3
     with pytest.raises(E.SopsError) as ei:
-        ctx.eval_batch(E.AGG, genomes["agg_evolved"], [(40, 9)], [1])
+        ctx.eval_batch(E.AGG, genomes["agg_evolved"], [(126, 9)], [1])
     assert ei.value.code == -4
 
 
@@ -247,18 +247,26 @@ def test_ragged_step_counts(ctx, genomes, rng_mode, kflag):
 
 
 @pytest.mark.parametrize("beh", [E.AGG, E.SEP, E.COAT, E.LOCO])
-def test_largest_supported_arena(ctx, genomes, beh, kflag):
-    # arena_layers 29 is the widest lattice the 64-bit rows hold (G + 4 = 63); one size above is refused
+def test_wide_and_largest_supported_arenas(ctx, genomes, beh, kflag):
+    # rows of 4 and 8 words (padded side <= 128 / 256) up to the widest lattice the u8 padded coordinates hold:
+    # arena_layers 125 (the reference's own u8 coordinates stop at 127); loco is defined up to 63 (u8 wrap upstream)
+    if kflag:
+        pytest.skip("the CTA variant is built for one- and two-word rows only")
     name = {E.AGG: "agg_random", E.SEP: "sep_random", E.COAT: "coat_random", E.LOCO: "loco_random"}[beh]
-    size = (29, 8, 4) if beh == E.COAT else (29, 20)
-    orient = np.asarray([[3]], dtype=np.uint8) if beh == E.LOCO else None
+    if beh == E.COAT:
+        sizes = [(40, 8, 4), (100, 10, 5), (125, 8, 4)]
+    elif beh == E.LOCO:
+        sizes = [(29, 20), (40, 20), (63, 25)]
+    else:
+        sizes = [(29, 20), (40, 20), (61, 30), (100, 30), (125, 20)]
+    seeds = list(range(7, 7 + len(sizes)))
+    orient = (np.arange(len(sizes)) % 3 + 1).astype(np.uint8).reshape(1, -1) if beh == E.LOCO else None
     for rng_mode in (E.RNG_VERIFY, E.RNG_FAST):
-        if rng_mode == E.RNG_VERIFY and kflag:
-            continue
-        got, want, cnt = run_pair(ctx, beh, genomes[name], [size], [7], rng_mode, steps=200000, orient=orient, flags=kflag)
-        check_equal(ctx, beh, genomes[name], [size], [7], got, want, cnt, rng_mode, 200000, orient=orient, flags=kflag)
+        got, want, cnt = run_pair(ctx, beh, genomes[name], sizes, seeds, rng_mode, steps=150000, orient=orient)
+        check_equal(ctx, beh, genomes[name], sizes, seeds, got, want, cnt, rng_mode, 150000, orient=orient)
+    too_big = (64, 20) if beh == E.LOCO else ((126, 8, 4) if beh == E.COAT else (126, 20))
     with pytest.raises(E.SopsError) as ei:
-        ctx.eval_batch(beh, genomes[name], [(30,) + size[1:]], [7])
+        ctx.eval_batch(beh, genomes[name], [too_big], [7])
     assert ei.value.code == -4
 
 
