@@ -295,6 +295,16 @@ def main():
         v_e = reduce(attempts_step, dist.ReduceOp.SUM if world > 1 else None) / (best[0] * 1e-3)
         extra["evolved_population"].update({"value": v_e, "unit": "attempts/s", "ms_per_step": best[0], "kernel": best[1],
                                             "generations_per_s": 1e3 / best[0], "mean_fitness": best[2]})
+        # the same GA generation with a population of 400 on ONE GPU (6000 chains): what a larger population gets
+        big = synthetic_genomes(rank * 400, 400, 48, args.gran)
+        ctx.prepare(E.AGG, big, tsz, tsd, gran=args.gran, rng_mode=mode)
+        ctx.launch(); ms_b = ctx.sync()
+        ctx.collect()
+        cb = ctx.counters()
+        extra["ga_generation_pop400_per_gpu"] = {
+            "value": reduce(float(cb["attempts"]), dist.ReduceOp.SUM if world > 1 else None) /
+                     (reduce(ms_b, dist.ReduceOp.MAX if world > 1 else None) * 1e-3),
+            "unit": "attempts/s", "ms_per_step": ms_b, "instances_per_gpu": 400 * len(tsz)}
         n_sweep, cap = 50000, 200000
         seeds = list(range(1 + rank * n_sweep, 1 + (rank + 1) * n_sweep))
         for nm, md in (("fast", E.RNG_FAST), ("verify", E.RNG_VERIFY)):
