@@ -67,3 +67,19 @@ def test_product_package_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, f
+
+
+def test_rust_binding_source_matches_header():
+    # rust/evosops-ffi cannot be compiled here (no cargo); keep its extern block in sync with the header by text
+    hdr = open(os.path.join(ROOT, "include", "evosops.h")).read()
+    rs = open(os.path.join(ROOT, "rust", "evosops-ffi", "src", "lib.rs")).read()
+    ext = rs[rs.index('extern "C" {'):]
+    ext = ext[:ext.index("\n}\n")]
+    for name, args in re.findall(r"fn (sops_[a-z_]+)\(([^;]*)\)", ext, flags=re.S):
+        m = re.search(r"\b%s\s*\(([^;]*)\);" % name, hdr, flags=re.S)
+        assert m, name
+        assert len([a for a in args.split(",") if a.strip()]) == len([a for a in m.group(1).split(",") if a.strip()]), name
+    for flag, val in re.findall(r"pub const (F_[A-Z_]+): u32 = (\d+);", rs):
+        assert re.search(r"SOPS_%s = %s\b" % (flag, val), hdr), flag
+    assert "pub arena: u16, pub layers: u16, pub coat: u16" in rs
+    assert "pub i0: u32, pub i1: u32, pub i2: u32, pub f: f32, pub norm: f64" in rs
