@@ -108,8 +108,12 @@ __device__ __forceinline__ uint32_t lowmask(uint32_t r) { return r >= 32 ? 0xfff
 // Predicated shared-memory updates: operands are computed by every lane (they are warp-uniform in the
 // commit path, so the work overlaps the repair arithmetic), only lanes with q set issue the access.
 __device__ __forceinline__ void pred_xor_shared(bool q, const uint32_t* addr, uint32_t mask) {
+    // the operands are pinned outside the predicated instruction so ptxas keeps ONE predicated ATOMS instead
+    // of sinking the address / mask arithmetic into a divergent branch (BSSY .. BSYNC costs ~35 cycles here)
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(addr), m = mask;
+    asm volatile("" : "+r"(a), "+r"(m));
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q red.shared.xor.b32 [%1], %2;\n\t}"
-                 :: "r"((uint32_t)q), "r"((uint32_t)__cvta_generic_to_shared(addr)), "r"(mask) : "memory");
+                 :: "r"((uint32_t)q), "r"(a), "r"(m) : "memory");
 }
 __device__ __forceinline__ void pred_store_u16(bool q, const uint16_t* addr, uint32_t v) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.shared.u16 [%1], %2;\n\t}"
@@ -366,16 +370,23 @@ __device__ __forceinline__ void commit_and_repair(const Lat& L, const Geo& g, ui
             }
             wrote = b1 | (b2 << 8);
         }
-        // addresses and masks are warp-uniform (sf, tf were broadcast); only lane f issues the three accesses
-        pred_xor_shared(mine, Plane<RW>::word(L.p0, sfr, sfc), 1u << (sfc & 31u));
-        pred_xor_shared(mine, Plane<RW>::word(L.p0, tfr, tfc), 1u << (tfc & 31u));
-        pred_store_u16(mine, L.pos + p.idx, tf);
     }
-    __syncwarp();
+    // AGG / COAT / LOCO lattice update: sf and tf were broadcast, so the two lattice words, their masks and the
+    // new values are warp-uniform.  Every lane performs the same read-modify-write (same address, same value:
+    // one wavefront, no divergence, no atomics): the loads are issued here, the stores after the window patch
+    // below, so the shared-memory latency hides behind that arithmetic.
+    uint32_t* ws = nullptr; uint32_t* wt = nullptr;
+    uint32_t wa = 0, wb = 0;
+    if (BEH != SEP) {
+        ws = const_cast<uint32_t*>(Plane<RW>::word(L.p0, sfr, sfc));
+        wt = const_cast<uint32_t*>(Plane<RW>::word(L.p0, tfr, tfc));
+        wa = *ws; wb = *wt;
+    }
     // ---- repair ----
     const uint32_t dU = win25_patch(sf, tf - sf, 0, p.s - 0x0202u);
     bool reread = (p.s == sf);                               // the moved particle itself was proposed again
     if (BEH == SEP) {
+        __syncwarp();
         if (x & 1) p.U0 ^= dU;
         if (x & 2) p.U1 ^= dU;
         reread |= (p.s == tf);                               // the swap partner was proposed
@@ -386,6 +397,15 @@ __device__ __forceinline__ void commit_and_repair(const Lat& L, const Geo& g, ui
             const uint32_t bs = (p.aux >> 8) & 0xff, bt = (p.aux >> 16) & 0xff;
             reread |= (b1 && (bs == b1 || bt == b1)) || (b2 && (bs == b2 || bt == b2));
         }
+        const uint32_t ms = 1u << (sfc & 31u), mt = 1u << (tfc & 31u);
+        if (ws == wt) {                                      // warp-uniform: both cells in one word
+            *ws = wa ^ ms ^ mt;
+        } else {
+            *ws = wa ^ ms;
+            *wt = wb ^ mt;
+        }
+        if (mine) L.pos[p.idx] = (uint16_t)tf;
+        __syncwarp();
     }
     if (active && lane > f && (dU != 0u || reread)) {
         if (reread) evaluate<BEH, RW>(L, g, p);
