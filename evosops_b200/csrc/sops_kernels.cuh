@@ -666,17 +666,31 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
             const uint32_t idxO = wy_mod_u64(rO, n, ms, kO), dO = wy_mod_u64(nE, 6, ms, kO + 1);
             const uint32_t PE = __ballot_sync(0xffffffffu, probe_possible<BEH, RW>(L, idxE, dE));
             const uint32_t PO = __ballot_sync(0xffffffffu, probe_possible<BEH, RW>(L, idxO, dO));
-            // which slots start a real step: a blocked step consumes 2 draws, a possible one 3
-            uint32_t realE = 0, realO = 0, l = 0, par = 0;
-            while (l < 31) {
-                uint32_t mm = ((par ? PO : PE) >> l) & ((1u << (31 - l)) - 1u);
-                uint32_t upto = mm ? l + (uint32_t)__ffs(mm) - 1 : 30u;
-                uint32_t mask = ((2u << upto) - 1u) & ~((1u << l) - 1u);
-                if (par) realO |= mask; else realE |= mask;
-                if (!mm) { l = 31; break; }
-                if (par) { l = upto + 2; par = 0; } else { l = upto + 1; par = 1; }
+            // Which slots start a real step: a blocked step consumes 2 draws, a possible one 3.  Walking lanes in
+            // order, the alignment is a 3-state automaton: E (the step starts in this lane's even slot), O (odd
+            // slot), S (no step starts here — an odd-slot possible step ran through; the next lane is E again).
+            //   E -> possible_E ? O : E      O -> possible_O ? S : O      S -> E
+            // Each lane's transition is a map on {E,O,S} (6 bits); the state on entry to lane l is the composition
+            // of the maps of lanes 0..l-1 applied to E: a warp scan over function composition (5 shuffle rounds)
+            // instead of a serial walk.
+            const uint32_t pe = (PE >> lane) & 1u, po = (PO >> lane) & 1u;
+            uint32_t map = pe | ((po ? 2u : 1u) << 2);       // image of E | image of O << 2 | image of S (= E = 0) << 4
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t first = __shfl_up_sync(0xffffffffu, map, off);   // composition of the block ending at lane - off
+                if (lane >= (uint32_t)off) {
+                    const uint32_t r0 = (map >> (2u * (first & 3u))) & 3u;
+                    const uint32_t r1 = (map >> (2u * ((first >> 2) & 3u))) & 3u;
+                    const uint32_t r2 = (map >> (2u * ((first >> 4) & 3u))) & 3u;
+                    map = r0 | (r1 << 2) | (r2 << 4);
+                }
             }
-            const uint32_t q_end = 2 * l + par;
+            const uint32_t entry = __shfl_up_sync(0xffffffffu, map, 1) & 3u;    // state after lane - 1, started from E
+            const uint32_t state = lane == 0 ? 0u : entry;
+            const uint32_t realE = __ballot_sync(0xffffffffu, state == 0u && lane < 31u);
+            const uint32_t realO = __ballot_sync(0xffffffffu, state == 1u && lane < 31u);
+            // draws consumed by lanes 0..30: 62 if the walk leaves lane 30 in E, 63 in O, 64 in S
+            const uint32_t q_end = 62u + (__shfl_sync(0xffffffffu, map, 30) & 3u);
             const bool myO = (realO >> lane) & 1u, myE = (realE >> lane) & 1u;
             const uint32_t ord = __popc((realE | realO) & lowmask(lane));
             const bool active = (myE || myO) && (uint64_t)ord < rem;
