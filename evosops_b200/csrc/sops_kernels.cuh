@@ -100,25 +100,8 @@ __host__ __device__ constexpr uint32_t dir_back5(int d) { return lift9((dir_word
 __host__ __device__ constexpr uint32_t dir_mid5(int d) { return lift9(dir_word(d) & 0x1ff, 0, 0); }
 __host__ __device__ constexpr uint32_t dir_front5(int d) { return lift9(dir_word(d) >> 18, dir_dr(d), dir_dc(d)); }
 __host__ __device__ constexpr uint32_t dir_tbit(int d) { return (uint32_t)(12 + 5 * dir_dr(d) + dir_dc(d)); }
-// 4-bit direction code (dr+1) | (dc+1) << 2, so that delta = (code & 3) + ((code >> 2) << 8) - 0x0101
-__host__ __device__ constexpr uint32_t dir_code(int d) { return (uint32_t)((dir_dr(d) + 1) | ((dir_dc(d) + 1) << 2)); }
 
 __device__ __forceinline__ uint32_t lowmask(uint32_t r) { return r >= 32 ? 0xffffffffu : ((1u << r) - 1u); }
-
-// Predicated shared-memory updates: operands are computed by every lane (they are warp-uniform in the
-// commit path, so the work overlaps the repair arithmetic), only lanes with q set issue the access.
-__device__ __forceinline__ void pred_xor_shared(bool q, const uint32_t* addr, uint32_t mask) {
-    // the operands are pinned outside the predicated instruction so ptxas keeps ONE predicated ATOMS instead
-    // of sinking the address / mask arithmetic into a divergent branch (BSSY .. BSYNC costs ~35 cycles here)
-    uint32_t a = (uint32_t)__cvta_generic_to_shared(addr), m = mask;
-    asm volatile("" : "+r"(a), "+r"(m));
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q red.shared.xor.b32 [%1], %2;\n\t}"
-                 :: "r"((uint32_t)q), "r"(a), "r"(m) : "memory");
-}
-__device__ __forceinline__ void pred_store_u16(bool q, const uint16_t* addr, uint32_t v) {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.shared.u16 [%1], %2;\n\t}"
-                 :: "r"((uint32_t)q), "r"((uint32_t)__cvta_generic_to_shared(addr)), "h"((uint16_t)v) : "memory");
-}
 
 // ------------------------------------------------------------------------------ bit planes ------
 // RW 32-bit words per row: 1 and 2 are specialised (PG <= 32 / 64), the generic form (4, 8) serves PG <= 128 / 256
@@ -165,13 +148,12 @@ __device__ __forceinline__ uint32_t win25(const uint32_t* p, uint32_t r, uint32_
            (Plane<RW>::seg(p, r + 1, c0, 31u) << 15) | (Plane<RW>::seg(p, r + 2, c0, 31u) << 20);
 }
 // XOR mask of the two flipped cells x and x + delta (a committed move) in the 5x5 window whose top-left
-// cell is `org` (= centre - 0x0202); kd = 5*dr + dc of the move.  Cells outside the window contribute 0.
-__device__ __forceinline__ uint32_t win25_patch(uint32_t x, uint32_t delta, int kd, uint32_t org) {
+// cell is `org` (= centre - 0x0202).  Cells outside the window contribute 0.
+__device__ __forceinline__ uint32_t win25_patch(uint32_t x, uint32_t delta, uint32_t org) {
     const uint32_t v = x - org;                              // (dr + 2) | (dc + 2) << 8 when inside
     const uint32_t w = v + delta;
     const bool vin = ((v | (v + 0x0303u)) & 0xFFFFF8F8u) == 0u;   // both fields in 0..4 (a borrow sets high bits)
     const bool win_ = ((w | (w + 0x0303u)) & 0xFFFFF8F8u) == 0u;
-    (void)kd;
     const uint32_t iv = (v & 7u) * 5u + (v >> 8), iw = (w & 7u) * 5u + (w >> 8);
     const uint32_t mv = 1u << (iv & 31u), mw = 1u << (iw & 31u);
     return (vin ? mv : 0u) ^ (win_ ? mw : 0u);
@@ -196,7 +178,7 @@ struct Geo {
 struct Lat {
     uint32_t* p0; uint32_t* p1; uint32_t* p2;
     uint16_t* pos; uint16_t* thr; uint16_t* light;
-    const uint4* dirtab;            // per direction: back5, mid5, front5 masks, delta | tbit << 16 | code << 24
+    const uint4* dirtab;            // per direction: back5, mid5, front5 masks, delta | tbit << 16
 };
 
 // locomotion.rs:260-290 on unpadded coordinates; light[b] = x | y << 8.  Beam id or -1 when the cell is on no beam.
@@ -224,8 +206,8 @@ __device__ __forceinline__ uint32_t same_mask(uint32_t w0, uint32_t w1, uint32_t
 struct Prop {
     uint32_t idx, d, pd;            // particle, direction, probability draw (0..999): fixed for the step
     uint32_t s, t;                  // packed padded source / target
-    uint32_t tt;                    // t | tbit << 16 | dir_code << 24 | SEP: flipped colour bits << 28 (what an accepted lane broadcasts)
-    uint32_t mB, mM, mF, tb;        // BACK / MID / FRONT masks in the 5x5 window, bit of the target cell | dir_code << 8
+    uint32_t tt;                    // t | tbit << 16 | SEP: flipped colour bits << 28 (what an accepted lane broadcasts)
+    uint32_t mB, mM, mF, tb;        // BACK / MID / FRONT masks in the 5x5 window, bit index of the target cell
     uint32_t U0;                    // 5x5 window of plane p0 around s
     uint32_t U1;                    // SEP: 5x5 window of plane p1.  COAT: object window (static)
     uint32_t aux;                   // LOCO: light_idx*48 | beam(s)+1 << 8 | beam(t)+1 << 16 | senses(s) << 24 | senses(t) << 25.  SEP: mover colour
@@ -290,7 +272,7 @@ template <int BEH, int RW>
 __device__ __forceinline__ void evaluate(const Lat& L, const Geo& g, Prop& p) {
     p.s = L.pos[p.idx];
     const uint4 dt = L.dirtab[p.d];
-    p.mB = dt.x; p.mM = dt.y; p.mF = dt.z; p.tb = dt.w >> 16;                // tbit | code << 8
+    p.mB = dt.x; p.mM = dt.y; p.mF = dt.z; p.tb = dt.w >> 16;
     p.t = (p.s + dt.w) & 0xffffu;
     p.tt = p.t | (dt.w & 0xffff0000u);
     const uint32_t sr = p.s & 0xff, sc = p.s >> 8, tr = p.t & 0xff, tc = p.t >> 8;
@@ -383,7 +365,7 @@ __device__ __forceinline__ void commit_and_repair(const Lat& L, const Geo& g, ui
         wa = *ws; wb = *wt;
     }
     // ---- repair ----
-    const uint32_t dU = win25_patch(sf, tf - sf, 0, p.s - 0x0202u);
+    const uint32_t dU = win25_patch(sf, tf - sf, p.s - 0x0202u);
     bool reread = (p.s == sf);                               // the moved particle itself was proposed again
     if (BEH == SEP) {
         __syncwarp();
@@ -752,7 +734,7 @@ __global__ void __launch_bounds__(256, SOPS_MIN_BLOCKS) sops_chain_kernel(const 
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int d = 0; d < 6; ++d)
-            s_dirtab[d] = make_uint4(dir_back5(d), dir_mid5(d), dir_front5(d), ((uint32_t)dir_delta(d) & 0xffffu) | (dir_tbit(d) << 16) | (dir_code(d) << 24));
+            s_dirtab[d] = make_uint4(dir_back5(d), dir_mid5(d), dir_front5(d), ((uint32_t)dir_delta(d) & 0xffffu) | (dir_tbit(d) << 16));
     }
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -787,7 +769,7 @@ __global__ void __launch_bounds__(256, SOPS_MIN_BLOCKS) sops_chain_kernel(const 
 template <int BEH>
 __device__ __forceinline__ bool patch_window(uint32_t sf, uint32_t ttf, uint32_t wrote, Prop& p, bool& reread) {
     const uint32_t tf = ttf & 0xffffu;
-    const uint32_t dU = win25_patch(sf, tf - sf, 0, p.s - 0x0202u);
+    const uint32_t dU = win25_patch(sf, tf - sf, p.s - 0x0202u);
     reread = (p.s == sf);                                    // the moved particle itself was proposed again
     if (BEH == SEP) {
         const uint32_t x = ttf >> 28;
@@ -890,7 +872,7 @@ __global__ void __launch_bounds__(32 * W) sops_chain_cta_kernel(const KParams P)
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int d = 0; d < 6; ++d)
-            s_dirtab[d] = make_uint4(dir_back5(d), dir_mid5(d), dir_front5(d), ((uint32_t)dir_delta(d) & 0xffffu) | (dir_tbit(d) << 16) | (dir_code(d) << 24));
+            s_dirtab[d] = make_uint4(dir_back5(d), dir_mid5(d), dir_front5(d), ((uint32_t)dir_delta(d) & 0xffffu) | (dir_tbit(d) << 16));
     }
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     Lat L;
