@@ -360,3 +360,32 @@ def test_full_size_sep_generation_properties(ctx, genomes):
     assert a[0]["norm"].mean() > 0.9                                          # the reference's evolved genome separates (0.95-0.98)
     b = ctx.eval_batch(E.SEP, gs, sizes, seeds, w1=0.65, w2=0.35, rng_mode=E.RNG_FAST)
     assert np.array_equal(a, b)
+
+
+def test_randomised_parity_sweep(ctx):
+    # property-style sweep: random behaviour / size / seeds / genome / step count / rng mode / kernel variant,
+    # final lattice + particle list + integers against the oracle each time (deterministic example stream)
+    rng = np.random.default_rng(20261019)
+    for case in range(40):
+        beh = int(rng.integers(0, 4))
+        a = int(rng.integers(4, 33))
+        if beh == E.COAT:
+            o = int(rng.integers(1, max(2, a // 4)))
+            c = int(rng.integers(1, max(2, (a - o) // 2)))
+            size = (a, o, c)
+            try:
+                E.instance_shape(beh, size)
+            except E.SopsError:
+                continue
+        else:
+            p = int(rng.integers(1, max(2, int(a * 0.75))))
+            size = (a, p)
+        gs = rng.integers(0, 11, size=(2, E.GENOME_LEN[beh]), dtype=np.uint8)
+        seeds = [int(rng.integers(0, 2 ** 63)), int(rng.integers(0, 2 ** 20))]
+        ms = rng.integers(0, 2 ** 63, size=(2, 2), dtype=np.uint64)
+        orient = rng.integers(1, 4, size=(2, 2)).astype(np.uint8) if beh == E.LOCO else None
+        steps = int(rng.integers(1, 120000))
+        rng_mode = int(rng.integers(0, 2))
+        kflag = E.F_FORCE_CTA if (rng_mode == E.RNG_FAST and a <= 29 and rng.integers(0, 2)) else 0
+        got, want, cnt = run_pair(ctx, beh, gs, [size, size], seeds, rng_mode, steps=steps, move_seeds=ms, orient=orient, flags=kflag)
+        check_equal(ctx, beh, gs, [size, size], seeds, got, want, cnt, rng_mode, steps, move_seeds=ms, orient=orient, flags=kflag)
