@@ -308,6 +308,22 @@ __device__ __forceinline__ bool probe_possible(const Lat& L, uint32_t idx, uint3
     return !(Plane<RW>::bit(L.p1, tr, tc) | Plane<RW>::bit(L.p0, tr, tc));
 }
 
+// warp-uniform flip of two cells of one plane (all lanes: same addresses, same values); `on` is uniform too
+template <int RW>
+__device__ __forceinline__ void flip_pair(uint32_t* plane, uint32_t sr, uint32_t sc, uint32_t tr, uint32_t tc, bool on) {
+    if (!on) return;
+    uint32_t* ws = const_cast<uint32_t*>(Plane<RW>::word(plane, sr, sc));
+    uint32_t* wt = const_cast<uint32_t*>(Plane<RW>::word(plane, tr, tc));
+    const uint32_t ms = 1u << (sc & 31u), mt = 1u << (tc & 31u);
+    if (ws == wt) {
+        *ws ^= ms ^ mt;
+    } else {
+        const uint32_t a = *ws, b = *wt;
+        *ws = a ^ ms;
+        *wt = b ^ mt;
+    }
+}
+
 // --- commit of lane f's accepted proposal + incremental repair of every later lane --------------------
 // Lane f flips its two cells (fire-and-forget shared reductions) and rewrites its position.  Every lane then
 // patches its register window with the flipped cells; a lane whose window really changed re-derives, a
@@ -335,21 +351,19 @@ __device__ __forceinline__ void commit_and_repair(const Lat& L, const Geo& g, ui
                 if (hit) { partner = base + __ffs(hit) - 1; break; }
             }
         }
-        if (mine) {
-            if (x & 1) { Plane<RW>::atom_xor(L.p0, sfr, sfc); Plane<RW>::atom_xor(L.p0, tfr, tfc); }
-            if (x & 2) { Plane<RW>::atom_xor(L.p1, sfr, sfc); Plane<RW>::atom_xor(L.p1, tfr, tfc); }
-            L.pos[idxf] = (uint16_t)tf;
-            if (kindf == 2) L.pos[partner] = (uint16_t)sf;
-        }
+        // every operand below is warp-uniform (broadcast, or the result of the scan): all lanes perform the
+        // same stores — no divergent region
+        flip_pair<RW>(L.p0, sfr, sfc, tfr, tfc, (x & 1u) != 0u);
+        flip_pair<RW>(L.p1, sfr, sfc, tfr, tfc, (x & 2u) != 0u);
+        L.pos[idxf] = (uint16_t)tf;
+        if (kindf == 2) L.pos[partner] = (uint16_t)sf;
     } else {
         if (BEH == LOCO) {                                   // locomotion.rs:344-519, net effect
             const uint32_t auxf = __shfl_sync(0xffffffffu, p.aux, f);
             const uint32_t b1 = ((auxf >> 24) & 1u) ? ((auxf >> 8) & 0xff) : 0u;      // beam fronts lane f rewrites
             const uint32_t b2 = ((auxf >> 25) & 1u) ? ((auxf >> 16) & 0xff) : 0u;
-            if (mine) {
-                if (b1) L.light[b1 - 1] = (uint16_t)((sfr - 2) | ((sfc - 2) << 8));
-                if (b2) L.light[b2 - 1] = (uint16_t)((tfr - 2) | ((tfc - 2) << 8));
-            }
+            if (b1) L.light[b1 - 1] = (uint16_t)((sfr - 2) | ((sfc - 2) << 8));        // warp-uniform branches and stores
+            if (b2) L.light[b2 - 1] = (uint16_t)((tfr - 2) | ((tfc - 2) << 8));
             wrote = b1 | (b2 << 8);
         }
     }
