@@ -345,11 +345,11 @@ __device__ __forceinline__ void commit_and_repair(const Lat& L, const Geo& g, ui
         if (kindf == 2) {
             // the partner's index: the reference's participants.iter().position scan (separation.rs:302),
             // here a warp-wide scan of the position list
-            for (uint32_t base = 0; base < g.n; base += 32) {
-                const uint32_t i = base + lane;
-                const uint32_t hit = __ballot_sync(0xffffffffu, i < g.n && L.pos[i] == tf);
-                if (hit) { partner = base + __ffs(hit) - 1; break; }
-            }
+            // (every lane scans its strided share with independent loads, one warp reduction at the end)
+            uint32_t found = 0xffffffffu;
+#pragma unroll 4
+            for (uint32_t i = lane; i < g.n; i += 32) if (L.pos[i] == tf) found = i;
+            partner = __reduce_min_sync(0xffffffffu, found);
         }
         // every operand below is warp-uniform (broadcast, or the result of the scan): all lanes perform the
         // same stores — no divergent region
