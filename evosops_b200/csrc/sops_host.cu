@@ -98,7 +98,7 @@ struct Group {                      // one kernel launch: instances of one row-w
     int rw;
     uint32_t first, count;          // range in the device's instance array
     uint32_t plane_words, pos_words, words_per_warp;
-    uint32_t off_p0, off_p1, off_p2, off_pos, off_thr, off_aux;
+    uint32_t off_p0, off_p1, off_p2, off_pos, off_thr, off_aux, off_tab;
     uint32_t dump_stride;
     size_t dump_off;                // word offset of this group's dump area
     int wpb, blocks;
@@ -228,6 +228,7 @@ void layout_group(Group& g, int beh, uint32_t max_pg, uint32_t max_n) {
     g.off_pos = off; off += g.pos_words;
     g.off_thr = off; off += thr_words;
     g.off_aux = off; if (beh == SOPS_LOCO) off += SOPS_LOCO_AUX_WORDS;
+    g.off_tab = off; if (beh == SOPS_AGG) off += SOPS_AGG_TAB_WORDS;
     off = (off + 1u) & ~1u;
     off |= 2u;                                                  // stride = 2 mod 4 words: spreads warps over banks, keeps 8-byte alignment
     g.words_per_warp = off;
@@ -545,7 +546,7 @@ int sops_batch_launch(sops_ctx* ctx) {
             kp.coat_dist = d.d_coat;
             kp.words_per_warp = g.words_per_warp;
             kp.off_p0 = g.off_p0; kp.off_p1 = g.off_p1; kp.off_p2 = g.off_p2;
-            kp.off_pos = g.off_pos; kp.off_thr = g.off_thr; kp.off_aux = g.off_aux;
+            kp.off_pos = g.off_pos; kp.off_thr = g.off_thr; kp.off_aux = g.off_aux; kp.off_tab = g.off_tab;
             kp.plane_words = g.plane_words; kp.pos_words = g.pos_words;
             kernel_fn fn = g.cta_w ? kernel_for_cta(ctx->behavior, g.rw) : kernel_for(ctx->behavior, g.rw, ctx->rng_mode);
             cudaStream_t st = d.stream;

@@ -59,6 +59,7 @@ struct KParams {
     // (PG = G + 4) so the 5x5 window of any particle stays inside the plane.
     uint32_t words_per_warp;
     uint32_t off_p0, off_p1, off_p2, off_pos, off_thr, off_aux;
+    uint32_t off_tab;               // AGG: hashed-window threshold table, SOPS_AGG_TAB_WORDS words
     uint32_t plane_words, pos_words;
 };
 
@@ -87,20 +88,54 @@ __host__ __device__ constexpr uint32_t dir_word(int d) {
 __host__ __device__ constexpr int dir_dr(int d) { return d == 0 || d == 4 ? -1 : d == 1 || d == 5 ? 1 : 0; }
 __host__ __device__ constexpr int dir_dc(int d) { return d == 2 || d == 4 ? -1 : d == 3 || d == 5 ? 1 : 0; }
 __host__ __device__ constexpr int dir_delta(int d) { return dir_dr(d) + 256 * dir_dc(d); }
-// The 5x5 window U around the source s (bit = 5*(dr+2) + (dc+2), s at bit 12) contains both 3x3 windows:
-// 3x3 bit (r, c) of the window centred at s + (or, oc) sits at U bit 5*(r+1+or) + (c+1+oc).
+// The 5x5 window U around the source s (bit = WS*(dr+2) + (dc+2), row stride WS = 6, s at bit 14) contains both
+// 3x3 windows: 3x3 bit (r, c) of the window centred at s + (or, oc) sits at U bit WS*(r+1+or) + (c+1+oc).
+// (Stride 6, not 5: with it every direction's 8 neighbourhood cells have a perfect multiplicative hash, below.)
+constexpr int WS = 6;
 __host__ __device__ constexpr uint32_t lift9(uint32_t m9, int orow, int ocol) {
     uint32_t m = 0;
     for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c)
-            if ((m9 >> (3 * r + c)) & 1u) m |= 1u << (5 * (r + 1 + orow) + (c + 1 + ocol));
+            if ((m9 >> (3 * r + c)) & 1u) m |= 1u << (WS * (r + 1 + orow) + (c + 1 + ocol));
     return m;
 }
 __host__ __device__ constexpr uint32_t dir_back5(int d) { return lift9((dir_word(d) >> 9) & 0x1ff, 0, 0); }
 __host__ __device__ constexpr uint32_t dir_mid5(int d) { return lift9(dir_word(d) & 0x1ff, 0, 0); }
 __host__ __device__ constexpr uint32_t dir_front5(int d) { return lift9(dir_word(d) >> 18, dir_dr(d), dir_dc(d)); }
-__host__ __device__ constexpr uint32_t dir_tbit(int d) { return (uint32_t)(12 + 5 * dir_dr(d) + dir_dc(d)); }
+__host__ __device__ constexpr uint32_t dir_tbit(int d) { return (uint32_t)(2 * WS + 2 + WS * dir_dr(d) + dir_dc(d)); }
+// Aggregation decides from the occupancy of the 8 cells around (s, t) only.  ((U & dir_all5) * dir_magic) >> 24 is a
+// perfect hash of those 8 bits (a bijection onto 0..255, checked at compile time), so the whole
+// back/mid/front popcount -> gene -> threshold chain (mod.rs:186-232, 284) becomes ONE multiply and ONE load from a
+// per-instance table [6][256] of thresholds that init_instance fills from the genome.
+__host__ __device__ constexpr uint32_t dir_all5(int d) { return dir_back5(d) | dir_mid5(d) | dir_front5(d); }
+__host__ __device__ constexpr uint32_t dir_magic(int d) {
+    return d == 0 ? 0x20102010u : d == 1 ? 0x00801024u : d == 2 ? 0x00080200u : d == 3 ? 0x00040100u : d == 4 ? 0x40202010u : 0x00400809u;
+}
+// k-th subset of a mask's set bits (software pdep)
+__host__ __device__ constexpr uint32_t deposit8(uint32_t k, uint32_t mask) {
+    uint32_t x = 0;
+    for (int b = 0; b < 8; ++b) {
+        const uint32_t low = mask & (0u - mask);
+        if ((k >> b) & 1u) x |= low;
+        mask ^= low;
+    }
+    return x;
+}
+__host__ __device__ constexpr bool magic_is_perfect(int d) {
+    uint32_t seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint32_t k = 0; k < 256; ++k) {
+        const uint32_t h = (deposit8(k, dir_all5(d)) * dir_magic(d)) >> 24;
+        if ((seen[h >> 5] >> (h & 31u)) & 1u) return false;
+        seen[h >> 5] |= 1u << (h & 31u);
+    }
+    return true;
+}
+static_assert(magic_is_perfect(0) && magic_is_perfect(1) && magic_is_perfect(2) && magic_is_perfect(3) &&
+              magic_is_perfect(4) && magic_is_perfect(5), "window hash must be a bijection for every direction");
+#define SOPS_AGG_TAB_WORDS (6u * 256u / 2u)                  // u16 thresholds, [direction][hash]
 
+// index of the most significant set bit (one FLO; 0xffffffff for 0) — for a one-hot mask, the index of its bit
+__device__ __forceinline__ uint32_t bfind32(uint32_t x) { uint32_t r; asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x)); return r; }
 __device__ __forceinline__ uint32_t lowmask(uint32_t r) { return r >= 32 ? 0xffffffffu : ((1u << r) - 1u); }
 
 // ------------------------------------------------------------------------------ bit planes ------
@@ -140,12 +175,12 @@ template <int RW>
 __device__ __forceinline__ uint32_t win9(const uint32_t* p, uint32_t r, uint32_t c) {
     return Plane<RW>::seg(p, r - 1, c - 1, 7u) | (Plane<RW>::seg(p, r, c - 1, 7u) << 3) | (Plane<RW>::seg(p, r + 1, c - 1, 7u) << 6);
 }
-// 5x5 window around padded cell (r, c): bit = 5*row + col.  r, c >= 2 always (two padding cells).
+// 5x5 window around padded cell (r, c): bit = WS*row + col.  r, c >= 2 always (two padding cells).
 template <int RW>
 __device__ __forceinline__ uint32_t win25(const uint32_t* p, uint32_t r, uint32_t c) {
     const uint32_t c0 = c - 2;
-    return Plane<RW>::seg(p, r - 2, c0, 31u) | (Plane<RW>::seg(p, r - 1, c0, 31u) << 5) | (Plane<RW>::seg(p, r, c0, 31u) << 10) |
-           (Plane<RW>::seg(p, r + 1, c0, 31u) << 15) | (Plane<RW>::seg(p, r + 2, c0, 31u) << 20);
+    return Plane<RW>::seg(p, r - 2, c0, 31u) | (Plane<RW>::seg(p, r - 1, c0, 31u) << WS) | (Plane<RW>::seg(p, r, c0, 31u) << (2 * WS)) |
+           (Plane<RW>::seg(p, r + 1, c0, 31u) << (3 * WS)) | (Plane<RW>::seg(p, r + 2, c0, 31u) << (4 * WS));
 }
 // XOR mask of the two flipped cells x and x + delta (a committed move) in the 5x5 window whose top-left
 // cell is `org` (= centre - 0x0202).  Cells outside the window contribute 0.
@@ -154,7 +189,7 @@ __device__ __forceinline__ uint32_t win25_patch(uint32_t x, uint32_t delta, uint
     const uint32_t w = v + delta;
     const bool vin = ((v | (v + 0x0303u)) & 0xFFFFF8F8u) == 0u;   // both fields in 0..4 (a borrow sets high bits)
     const bool win_ = ((w | (w + 0x0303u)) & 0xFFFFF8F8u) == 0u;
-    const uint32_t iv = (v & 7u) * 5u + (v >> 8), iw = (w & 7u) * 5u + (w >> 8);
+    const uint32_t iv = (v & 7u) * (uint32_t)WS + (v >> 8), iw = (w & 7u) * (uint32_t)WS + (w >> 8);
     const uint32_t mv = 1u << (iv & 31u), mw = 1u << (iw & 31u);
     return (vin ? mv : 0u) ^ (win_ ? mw : 0u);
 }
@@ -178,8 +213,16 @@ struct Geo {
 struct Lat {
     uint32_t* p0; uint32_t* p1; uint32_t* p2;
     uint16_t* pos; uint16_t* thr; uint16_t* light;
+    uint16_t* tab;                  // AGG: thresholds by [direction][window hash]
     const uint4* dirtab;            // per direction: back5, mid5, front5 masks, delta | tbit << 16
+                                    // (AGG: all-8-cells mask, hash multiplier, table offset, delta | tbit << 16)
 };
+template <int BEH>
+__device__ __forceinline__ uint4 dirtab_entry(int d) {
+    const uint32_t w = ((uint32_t)dir_delta(d) & 0xffffu) | (dir_tbit(d) << 16);
+    if (BEH == AGG) return make_uint4(dir_all5(d), dir_magic(d), (uint32_t)d << 8, w);
+    return make_uint4(dir_back5(d), dir_mid5(d), dir_front5(d), w);
+}
 
 // locomotion.rs:260-290 on unpadded coordinates; light[b] = x | y << 8.  Beam id or -1 when the cell is on no beam.
 __device__ __forceinline__ int loco_beam(uint32_t o, int a, int x, int y) {
@@ -208,6 +251,7 @@ struct Prop {
     uint32_t s, t;                  // packed padded source / target
     uint32_t tt;                    // t | tbit << 16 | SEP: flipped colour bits << 28 (what an accepted lane broadcasts)
     uint32_t mB, mM, mF, tb;        // BACK / MID / FRONT masks in the 5x5 window, bit index of the target cell
+                                    // (AGG: mB = mask of all 8 cells, mM = hash multiplier, mF = table offset)
     uint32_t U0;                    // 5x5 window of plane p0 around s
     uint32_t U1;                    // SEP: 5x5 window of plane p1.  COAT: object window (static)
     uint32_t aux;                   // LOCO: light_idx*48 | beam(s)+1 << 8 | beam(t)+1 << 16 | senses(s) << 24 | senses(t) << 25.  SEP: mover colour
@@ -225,9 +269,18 @@ __device__ __forceinline__ uint32_t same_mask25(uint32_t w0, uint32_t w1, uint32
 // decision from the registers (window, static flag, draws): no lattice access, one or two threshold loads
 template <int BEH>
 __device__ __forceinline__ void derive(const Lat& L, const Geo& g, Prop& p) {
-    if (BEH == AGG || BEH == LOCO) {
+    if (BEH == AGG) {
+        // hashed window -> threshold: one multiply, one load (table built by init_instance)
+        // (integer arithmetic up to ONE final compare: chained predicates cost ~13 cycles each on the commit path,
+        // and the load must not wait for the possible-ness test)
+        const uint32_t thr = L.tab[p.mF + (((p.U0 & p.mB) * p.mM) >> 24)];
+        const uint32_t blocked = (uint32_t)p.bstat | ((p.U0 >> (p.tb & 31u)) & 1u);   // mod.rs:235-251
+        p.poss = blocked == 0u;
+        p.kind = p.poss ? 1u : 0u;
+        p.eff = p.pd < (thr & (blocked - 1u));               // mod.rs:284-285: possible and draw below the threshold
+    } else if (BEH == LOCO) {
         uint32_t gi = (__popc(p.U0 & p.mB) * 3 + __popc(p.U0 & p.mM)) * 4 + __popc(p.U0 & p.mF);
-        if (BEH == LOCO) gi += p.aux & 0xffu;
+        gi += p.aux & 0xffu;
         const uint32_t thr = L.thr[gi];
         p.poss = !p.bstat && !((p.U0 >> (p.tb & 31u)) & 1u);         // mod.rs:235-251
         p.kind = p.poss ? 1u : 0u;
@@ -267,9 +320,9 @@ __device__ __forceinline__ void derive(const Lat& L, const Geo& g, Prop& p) {
     }
 }
 
-// full evaluation of a proposal against the current lattice: position, window, static flag, decision
+// what a proposal reads from the current lattice: position, window(s), static flag
 template <int BEH, int RW>
-__device__ __forceinline__ void evaluate(const Lat& L, const Geo& g, Prop& p) {
+__device__ __forceinline__ void load_proposal(const Lat& L, const Geo& g, Prop& p) {
     p.s = L.pos[p.idx];
     const uint4 dt = L.dirtab[p.d];
     p.mB = dt.x; p.mM = dt.y; p.mF = dt.z; p.tb = dt.w >> 16;
@@ -295,6 +348,11 @@ __device__ __forceinline__ void evaluate(const Lat& L, const Geo& g, Prop& p) {
             p.aux = li * 48u | ((uint32_t)(bs + 1) << 8) | ((uint32_t)(bt + 1) << 16) | (cur << 24) | (fut << 25);
         }
     }
+}
+// full evaluation of a proposal against the current lattice: position, window, static flag, decision
+template <int BEH, int RW>
+__device__ __forceinline__ void evaluate(const Lat& L, const Geo& g, Prop& p) {
+    load_proposal<BEH, RW>(L, g, p);
     derive<BEH>(L, g, p);
 }
 
@@ -409,12 +467,74 @@ __device__ __forceinline__ void commit_and_repair(const Lat& L, const Geo& g, ui
     }
 }
 
+// --- aggregation: straight-line commit rounds ---------------------------------------------------------------
+// Same protocol as resolve_batch below, arranged so one commit round is branch-free:
+//   * every lane re-derives after every commit (AGG's decision is one multiply + one load, cheaper than a divergent
+//     "touched lanes only" region); lanes at or before the committing lane keep the window they retired with, and a
+//     lane that committed (or is inactive) carries pd = 0xffffffff, which no threshold exceeds;
+//   * a lane that proposed the particle that just moved is STALE: it joins the candidate set and is re-evaluated from
+//     the lattice when it becomes the lowest candidate (everything before it is committed by then) — a warp-uniform,
+//     rare branch instead of a divergent region in every round;
+//   * the lowest candidate of the NEXT round is selected and its move broadcast before the loop branch, so the
+//     vote -> branch latency hides behind the find-first-set and the shuffles;
+//   * the lattice update is two warp-uniform read-modify-writes (all lanes: same address, same value), also when
+//     both cells share a word.
+template <int RW, bool VERIFY>
+__device__ __forceinline__ uint32_t resolve_batch_agg(const Lat& L, const Geo& g, uint32_t lane, bool active, Prop& p, uint32_t& ncommit) {
+    uint32_t R = 32;
+    uint32_t stale = 0;                                      // warp-uniform lane mask
+    // VERIFY: a lane below the cut R still has the possible-ness it was aligned with (a flip cuts the batch there)
+    const bool poss0 = p.poss;
+    uint32_t A = __ballot_sync(0xffffffffu, p.eff);
+    uint32_t low = A & (0u - A);                             // lowest candidate as a one-hot mask (0: none)
+    uint32_t f = bfind32(low);
+    uint32_t sf = __shfl_sync(0xffffffffu, p.s, f);
+    uint32_t ttf = __shfl_sync(0xffffffffu, p.tt, f);
+    bool is_stale = false;
+    while (low) {
+        if (is_stale) {                                      // warp-uniform, rare
+            if (lane == f) load_proposal<AGG, RW>(L, g, p);
+            stale ^= low;
+        } else {
+            const uint32_t tf = ttf & 0xffffu;
+            const uint32_t sfr = sf & 0xff, sfc = sf >> 8, tfr = tf & 0xff, tfc = tf >> 8;
+            uint32_t* ws = const_cast<uint32_t*>(Plane<RW>::word(L.p0, sfr, sfc));
+            uint32_t* wt = const_cast<uint32_t*>(Plane<RW>::word(L.p0, tfr, tfc));
+            const uint32_t wa = *ws, wb = *wt;
+            const uint32_t dU = win25_patch(sf, tf - sf, p.s - 0x0202u);
+            p.U0 ^= lane > f ? dU : 0u;
+            stale |= __ballot_sync(0xffffffffu, active && lane > f && p.s == sf);   // proposed the moved particle again
+            const uint32_t ms = 1u << (sfc & 31u), mt = 1u << (tfc & 31u);
+            const uint32_t same = ws == wt ? 0xffffffffu : 0u;
+            *ws = wa ^ ms ^ (mt & same);
+            *wt = wb ^ mt ^ (ms & same);
+            if (lane == f) { L.pos[p.idx] = (uint16_t)tf; p.pd = 0xffffffffu; }
+            ++ncommit;
+        }
+        __syncwarp();
+        derive<AGG>(L, g, p);
+        if (VERIFY) {
+            const uint32_t X = __ballot_sync(0xffffffffu, active && p.poss != poss0) & lowmask(R) & ~stale;
+            if (X) R = (uint32_t)__ffs(X) - 1;
+        }
+        A = __ballot_sync(0xffffffffu, p.eff) | stale;
+        if (VERIFY) A &= lowmask(R);
+        low = A & (0u - A);
+        is_stale = (low & stale) != 0u;
+        f = bfind32(low);
+        sf = __shfl_sync(0xffffffffu, p.s, f);
+        ttf = __shfl_sync(0xffffffffu, p.tt, f);
+    }
+    return R;
+}
+
 // --- commit rounds of one speculative batch ---------------------------------------------------------------
 // On entry every active lane holds a proposal evaluated against the current lattice; lane order = chain
 // order.  VERIFY: a repair that flips a lane's possible-ness changes how many draws that step consumes, so
 // the batch is cut at that lane (returned bound R; lanes >= R are not retired).  ncommit is warp-uniform.
 template <int BEH, int RW, bool VERIFY>
 __device__ __forceinline__ uint32_t resolve_batch(const Lat& L, const Geo& g, uint32_t lane, bool active, Prop& p, uint32_t& ncommit) {
+    if (BEH == AGG) return resolve_batch_agg<RW, VERIFY>(L, g, lane, active, p, ncommit);
     uint32_t R = 32;
     for (;;) {
         uint32_t A = __ballot_sync(0xffffffffu, p.eff);
@@ -567,6 +687,20 @@ __device__ __forceinline__ uint32_t init_instance(const KParams& P, const Lat& L
     const uint8_t* gen = P.genomes + (size_t)in.genome * P.genome_len;
     for (uint32_t k = lane; k < P.genome_len; k += 32) L.thr[k] = P.prob[gen[k] & 15];
     __syncwarp();
+    if (BEH == AGG) {
+        // threshold of every occupancy pattern of the 8 cells around (s, t), per direction, stored at the pattern's
+        // hash: gene index [back][mid][front] as in mod.rs:186-232
+        for (uint32_t k = lane; k < 6u * 256u; k += 32) {
+            const uint32_t d = k >> 8;
+            const uint4 dt = L.dirtab[d];
+            const uint32_t mB = d == 0 ? dir_back5(0) : d == 1 ? dir_back5(1) : d == 2 ? dir_back5(2) : d == 3 ? dir_back5(3) : d == 4 ? dir_back5(4) : dir_back5(5);
+            const uint32_t mM = d == 0 ? dir_mid5(0) : d == 1 ? dir_mid5(1) : d == 2 ? dir_mid5(2) : d == 3 ? dir_mid5(3) : d == 4 ? dir_mid5(4) : dir_mid5(5);
+            const uint32_t x = deposit8(k & 255u, dt.x);
+            const uint32_t nb = __popc(x & mB), nm = __popc(x & mM), nf = __popc(x & ~(mB | mM));
+            L.tab[dt.z + ((x * dt.y) >> 24)] = L.thr[(nb * 3 + nm) * 4 + nf];
+        }
+        __syncwarp();
+    }
     return status;
 }
 
@@ -639,6 +773,7 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
         }
         if (tail) {
             const bool active = lane < tail;
+            if (!active) cur.pd = 0xffffffffu;               // never accepted, also when AGG re-derives after a commit
             evaluate<BEH, RW>(L, g, cur);
             if (!active) { cur.eff = false; cur.poss = false; }
             resolve_batch<BEH, RW, false>(L, g, lane, active, cur, ncommit);
@@ -694,6 +829,7 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
             p.idx = myO ? idxO : idxE; p.d = myO ? dO : dE;
             // the probability draw exists only for a possible step; computing it for every lane is harmless
             p.pd = wy_mod_1000(myO ? nO32 : (uint32_t)nE, ms, (myO ? kO : kE) + 2);
+            if (!active) p.pd = 0xffffffffu;                 // never accepted, also when AGG re-derives after a commit
             evaluate<BEH, RW>(L, g, p);
             if (!active) { p.eff = false; p.poss = false; }
             const uint32_t am = __ballot_sync(0xffffffffu, active);
@@ -748,7 +884,7 @@ __global__ void __launch_bounds__(256, SOPS_MIN_BLOCKS) sops_chain_kernel(const 
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int d = 0; d < 6; ++d)
-            s_dirtab[d] = make_uint4(dir_back5(d), dir_mid5(d), dir_front5(d), ((uint32_t)dir_delta(d) & 0xffffu) | (dir_tbit(d) << 16));
+            s_dirtab[d] = dirtab_entry<BEH>(d);
     }
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -758,6 +894,7 @@ __global__ void __launch_bounds__(256, SOPS_MIN_BLOCKS) sops_chain_kernel(const 
     L.pos = reinterpret_cast<uint16_t*>(base + P.off_pos);
     L.thr = reinterpret_cast<uint16_t*>(base + P.off_thr);
     L.light = reinterpret_cast<uint16_t*>(base + P.off_aux);
+    L.tab = reinterpret_cast<uint16_t*>(base + P.off_tab);
     L.dirtab = s_dirtab;
     for (;;) {
         uint32_t q = 0;
@@ -886,7 +1023,7 @@ __global__ void __launch_bounds__(32 * W) sops_chain_cta_kernel(const KParams P)
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int d = 0; d < 6; ++d)
-            s_dirtab[d] = make_uint4(dir_back5(d), dir_mid5(d), dir_front5(d), ((uint32_t)dir_delta(d) & 0xffffu) | (dir_tbit(d) << 16));
+            s_dirtab[d] = dirtab_entry<BEH>(d);
     }
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     Lat L;
@@ -894,6 +1031,7 @@ __global__ void __launch_bounds__(32 * W) sops_chain_cta_kernel(const KParams P)
     L.pos = reinterpret_cast<uint16_t*>(smem + P.off_pos);
     L.thr = reinterpret_cast<uint16_t*>(smem + P.off_thr);
     L.light = reinterpret_cast<uint16_t*>(smem + P.off_aux);
+    L.tab = reinterpret_cast<uint16_t*>(smem + P.off_tab);
     L.dirtab = s_dirtab;
     for (;;) {
         __syncthreads();                                     // previous instance fully retired (s_q, lattice reusable)
