@@ -469,7 +469,7 @@ int sops_batch_prepare(sops_ctx* ctx, int behavior, const uint8_t* genomes, uint
                 kernel_fn fn = kernel_for_cta(behavior, grp.rw);
                 grp.wpb = grp.cta_w;
                 grp.smem = smem_per_warp;
-                if (grp.smem > 48 * 1024)
+                if (grp.smem + 1024 > 48 * 1024)                   // + the kernels' static shared memory
                     CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grp.smem));
                 CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, grp.cta_w * 32, grp.smem));
                 if (per_sm < 1) return fail(ctx, SOPS_E_UNSUPPORTED, "instance does not fit in shared memory");
@@ -483,7 +483,7 @@ int sops_batch_prepare(sops_ctx* ctx, int behavior, const uint8_t* genomes, uint
                 if (wpb < 1) wpb = 1;
                 grp.wpb = wpb;
                 grp.smem = smem_per_warp * (size_t)wpb;
-                if (grp.smem > 48 * 1024)
+                if (grp.smem + 1024 > 48 * 1024)                   // + the kernels' static shared memory
                     CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grp.smem));
                 CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, wpb * 32, grp.smem));
                 if (per_sm < 1) return fail(ctx, SOPS_E_UNSUPPORTED, "instance does not fit in shared memory");
@@ -547,6 +547,7 @@ int sops_batch_launch(sops_ctx* ctx) {
             kp.words_per_warp = g.words_per_warp;
             kp.off_p0 = g.off_p0; kp.off_p1 = g.off_p1; kp.off_p2 = g.off_p2;
             kp.off_pos = g.off_pos; kp.off_thr = g.off_thr; kp.off_aux = g.off_aux; kp.off_tab = g.off_tab;
+            { const char* v = getenv("SOPS_AGG_VARIANT"); kp.variant = v ? (uint32_t)atoi(v) : 0u; }
             kp.plane_words = g.plane_words; kp.pos_words = g.pos_words;
             kernel_fn fn = g.cta_w ? kernel_for_cta(ctx->behavior, g.rw) : kernel_for(ctx->behavior, g.rw, ctx->rng_mode);
             cudaStream_t st = d.stream;

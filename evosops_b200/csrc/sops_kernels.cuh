@@ -60,6 +60,7 @@ struct KParams {
     uint32_t words_per_warp;
     uint32_t off_p0, off_p1, off_p2, off_pos, off_thr, off_aux;
     uint32_t off_tab;               // AGG: hashed-window threshold table, SOPS_AGG_TAB_WORDS words
+    uint32_t variant;               // AGG: 0 = straight-line commit rounds, 1 = "touched lanes only" rounds
     uint32_t plane_words, pos_words;
 };
 
@@ -214,6 +215,7 @@ struct Lat {
     uint32_t* p0; uint32_t* p1; uint32_t* p2;
     uint16_t* pos; uint16_t* thr; uint16_t* light;
     uint16_t* tab;                  // AGG: thresholds by [direction][window hash]
+    uint32_t variant;
     const uint4* dirtab;            // per direction: back5, mid5, front5 masks, delta | tbit << 16
                                     // (AGG: all-8-cells mask, hash multiplier, table offset, delta | tbit << 16)
 };
@@ -468,49 +470,65 @@ __device__ __forceinline__ void commit_and_repair(const Lat& L, const Geo& g, ui
 }
 
 // --- aggregation: straight-line commit rounds ---------------------------------------------------------------
-// Same protocol as resolve_batch below, arranged so one commit round is branch-free:
+// Same protocol as resolve_batch below, arranged so one commit round is branch-free and short.  A chain that accepts
+// often is bound by the instructions ONE warp can issue per round (integer ops: one per two cycles), so the round
+// is written for instruction count:
 //   * every lane re-derives after every commit (AGG's decision is one multiply + one load, cheaper than a divergent
 //     "touched lanes only" region); lanes at or before the committing lane keep the window they retired with, and a
 //     lane that committed (or is inactive) carries pd = 0xffffffff, which no threshold exceeds;
 //   * a lane that proposed the particle that just moved is STALE: it joins the candidate set and is re-evaluated from
 //     the lattice when it becomes the lowest candidate (everything before it is committed by then) — a warp-uniform,
 //     rare branch instead of a divergent region in every round;
-//   * the lowest candidate of the NEXT round is selected and its move broadcast before the loop branch, so the
-//     vote -> branch latency hides behind the find-first-set and the shuffles;
-//   * the lattice update is two warp-uniform read-modify-writes (all lanes: same address, same value), also when
-//     both cells share a word.
+//   * the committing lane updates the lattice itself: predicated loads and stores (no atomics: ptxas wraps a predicated
+//     shared atomic in a divergent region) on word addresses and masks every lane prepared once per batch from its
+//     OWN proposal — nothing is recomputed from the broadcast move, the loads are issued before the broadcast returns;
+//   * the lowest candidate of the next round is selected (one find-leading-one on the isolated lowest bit) and its
+//     move broadcast before the loop branch, so the vote -> branch latency hides behind them.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// the committing lane's own lattice update, in two halves so the loads can be issued early
+__device__ __forceinline__ void own_cells_load(uint32_t lane, uint32_t f, uint32_t a_ws, uint32_t a_wt, uint32_t& w0, uint32_t& w1) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.eq.u32 q, %2, %3;\n\t"
+        "@q ld.shared.b32 %0, [%4];\n\t"
+        "@q ld.shared.b32 %1, [%5];\n\t}"
+        : "+r"(w0), "+r"(w1) : "r"(lane), "r"(f), "r"(a_ws), "r"(a_wt) : "memory");
+}
+__device__ __forceinline__ void own_cells_store(uint32_t lane, uint32_t f, uint32_t a_ws, uint32_t a_wt, uint32_t a_pos,
+                                                uint32_t v0, uint32_t v1, uint32_t t) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.eq.u32 q, %0, %1;\n\t"
+        "@q st.shared.b32 [%2], %3;\n\t"
+        "@q st.shared.b32 [%4], %5;\n\t"
+        "@q st.shared.u16 [%6], %7;\n\t}"
+        :: "r"(lane), "r"(f), "r"(a_ws), "r"(v0), "r"(a_wt), "r"(v1), "r"(a_pos), "h"((uint16_t)t) : "memory");
+}
+
 template <int RW, bool VERIFY>
 __device__ __forceinline__ uint32_t resolve_batch_agg(const Lat& L, const Geo& g, uint32_t lane, bool active, Prop& p, uint32_t& ncommit) {
+    constexpr bool PAIR = !VERIFY;                           // commit two candidates per round when they cannot interact
     uint32_t R = 32;
     uint32_t stale = 0;                                      // warp-uniform lane mask
     // VERIFY: a lane below the cut R still has the possible-ness it was aligned with (a flip cuts the batch there)
     const bool poss0 = p.poss;
     uint32_t A = __ballot_sync(0xffffffffu, p.eff);
     uint32_t low = A & (0u - A);                             // lowest candidate as a one-hot mask (0: none)
-    uint32_t f = bfind32(low);
-    uint32_t sf = __shfl_sync(0xffffffffu, p.s, f);
-    uint32_t ttf = __shfl_sync(0xffffffffu, p.tt, f);
-    bool is_stale = false;
-    while (low) {
-        if (is_stale) {                                      // warp-uniform, rare
-            if (lane == f) load_proposal<AGG, RW>(L, g, p);
-            stale ^= low;
-        } else {
-            const uint32_t tf = ttf & 0xffffu;
-            const uint32_t sfr = sf & 0xff, sfc = sf >> 8, tfr = tf & 0xff, tfc = tf >> 8;
-            uint32_t* ws = const_cast<uint32_t*>(Plane<RW>::word(L.p0, sfr, sfc));
-            uint32_t* wt = const_cast<uint32_t*>(Plane<RW>::word(L.p0, tfr, tfc));
-            const uint32_t wa = *ws, wb = *wt;
-            const uint32_t dU = win25_patch(sf, tf - sf, p.s - 0x0202u);
-            p.U0 ^= lane > f ? dU : 0u;
-            stale |= __ballot_sync(0xffffffffu, active && lane > f && p.s == sf);   // proposed the moved particle again
-            const uint32_t ms = 1u << (sfc & 31u), mt = 1u << (tfc & 31u);
-            const uint32_t same = ws == wt ? 0xffffffffu : 0u;
-            *ws = wa ^ ms ^ (mt & same);
-            *wt = wb ^ mt ^ (ms & same);
-            if (lane == f) { L.pos[p.idx] = (uint16_t)tf; p.pd = 0xffffffffu; }
-            ++ncommit;
-        }
+    if (!low) return R;
+    const uint32_t lane_g = active ? lane : 0u;              // an inactive lane is never "later than f": never patched, never stale
+    // this lane's own commit, prepared once: word addresses and bit masks of its two cells, its position slot
+    uint32_t a_ws, a_wt, m_s, m_t, org;
+    const uint32_t a_pos = smem_addr(L.pos + p.idx);
+    auto prepare = [&]() {
+        a_ws = smem_addr(Plane<RW>::word(L.p0, p.s & 0xff, p.s >> 8));
+        a_wt = smem_addr(Plane<RW>::word(L.p0, p.t & 0xff, p.t >> 8));
+        m_s = 1u << ((p.s >> 8) & 31u);
+        m_t = 1u << ((p.t >> 8) & 31u);
+        if (a_ws == a_wt) m_s = m_t = m_s ^ m_t;             // both cells in one word: the two stores write the same value
+        org = p.s - 0x0202u;
+    };
+    auto revote = [&]() {
         __syncwarp();
         derive<AGG>(L, g, p);
         if (VERIFY) {
@@ -520,10 +538,79 @@ __device__ __forceinline__ uint32_t resolve_batch_agg(const Lat& L, const Geo& g
         A = __ballot_sync(0xffffffffu, p.eff) | stale;
         if (VERIFY) A &= lowmask(R);
         low = A & (0u - A);
-        is_stale = (low & stale) != 0u;
-        f = bfind32(low);
-        sf = __shfl_sync(0xffffffffu, p.s, f);
-        ttf = __shfl_sync(0xffffffffu, p.tt, f);
+    };
+    prepare();
+    while (low) {
+        const uint32_t f1 = bfind32(low);
+        if (low & stale) {                                   // warp-uniform, rare: re-read, then it is an ordinary candidate
+            if (lane == f1) { load_proposal<AGG, RW>(L, g, p); prepare(); }
+            stale ^= low;
+            revote();
+            continue;
+        }
+        // second-lowest candidate: committed in the same round when the two moves cannot interact
+        uint32_t low2 = 0;
+        if (PAIR) { const uint32_t rest = A ^ low; low2 = rest & (0u - rest) & ~stale; }
+        const uint32_t f2r = bfind32(low2);                  // 0xffffffff for "none": shuffles then read lane 31, unused
+        uint32_t w0 = 0, w1 = 0;
+        own_cells_load(lane, f1, a_ws, a_wt, w0, w1);
+        const uint32_t sf1 = __shfl_sync(0xffffffffu, p.s, f1);
+        const uint32_t tf1 = __shfl_sync(0xffffffffu, p.tt, f1) & 0xffffu;
+        uint32_t sf2 = 0, tf2 = 0, f2 = 0xffffffffu;
+        if (PAIR) {
+            sf2 = __shfl_sync(0xffffffffu, p.s, f2r);
+            tf2 = __shfl_sync(0xffffffffu, p.tt, f2r) & 0xffffu;
+            // c1 flips cells within distance 1 of sf1; c2 decides from cells within distance 2 of sf2: with the two
+            // sources more than 3 apart (Chebyshev) neither move can change the other's decision or particle
+            const uint32_t dd = sf1 - sf2 + 0x0303u;
+            const bool near = ((dd | (dd + 0x0101u)) & 0xFFFFF8F8u) == 0u;
+            if (near) low2 = 0;
+            f2 = low2 ? f2r : 0xffffffffu;
+        }
+        const bool later1 = lane_g > f1, later2 = PAIR && lane_g > f2;
+        uint32_t dU1 = win25_patch(sf1, tf1 - sf1, org);
+        asm volatile("" : "+r"(dU1));                        // keep the patch arithmetic out of a divergent branch
+        dU1 = later1 ? dU1 : 0u;
+        uint32_t dU2 = 0;
+        if (PAIR) {
+            dU2 = win25_patch(sf2, tf2 - sf2, org);
+            asm volatile("" : "+r"(dU2));
+            dU2 = later2 ? dU2 : 0u;
+        }
+        const uint32_t st1 = __ballot_sync(0xffffffffu, later1 && p.s == sf1);   // proposed the moved particle again
+        const uint32_t st2 = PAIR ? __ballot_sync(0xffffffffu, later2 && p.s == sf2) : 0u;
+        p.U0 ^= dU1 ^ dU2;
+        own_cells_store(lane, f1, a_ws, a_wt, a_pos, w0 ^ m_s, w1 ^ m_t, p.t);
+        p.pd = lane == f1 ? 0xffffffffu : p.pd;
+        uint32_t x0 = 0, x1 = 0;
+        if (PAIR) own_cells_load(lane, f2, a_ws, a_wt, x0, x1);   // after c1's stores: the two moves may share a word
+        stale |= st1;
+        ++ncommit;
+        __syncwarp();
+        derive<AGG>(L, g, p);
+        if (VERIFY) {
+            const uint32_t X = __ballot_sync(0xffffffffu, active && p.poss != poss0) & lowmask(R) & ~stale;
+            if (X) R = (uint32_t)__ffs(X) - 1;
+        }
+        const uint32_t E = __ballot_sync(0xffffffffu, p.eff);
+        if (PAIR && low2) {
+            // lanes strictly between the two: they saw c1 only; if one of them is a candidate now it precedes c2
+            const uint32_t between = (low2 - 1u) & ~(low | (low - 1u));
+            if ((E | stale) & between) {                     // rare: undo c2's patch, it is selected again later
+                p.U0 ^= dU2;
+                revote();
+                continue;
+            }
+            own_cells_store(lane, f2, a_ws, a_wt, a_pos, x0 ^ m_s, x1 ^ m_t, p.t);
+            p.pd = lane == f2 ? 0xffffffffu : p.pd;
+            stale |= st2;
+            ++ncommit;
+            A = (E & ~low2) | stale;
+        } else {
+            A = E | stale;
+        }
+        if (VERIFY) A &= lowmask(R);
+        low = A & (0u - A);
     }
     return R;
 }
@@ -534,7 +621,7 @@ __device__ __forceinline__ uint32_t resolve_batch_agg(const Lat& L, const Geo& g
 // the batch is cut at that lane (returned bound R; lanes >= R are not retired).  ncommit is warp-uniform.
 template <int BEH, int RW, bool VERIFY>
 __device__ __forceinline__ uint32_t resolve_batch(const Lat& L, const Geo& g, uint32_t lane, bool active, Prop& p, uint32_t& ncommit) {
-    if (BEH == AGG) return resolve_batch_agg<RW, VERIFY>(L, g, lane, active, p, ncommit);
+    if (BEH == AGG && L.variant == 0) return resolve_batch_agg<RW, VERIFY>(L, g, lane, active, p, ncommit);
     uint32_t R = 32;
     for (;;) {
         uint32_t A = __ballot_sync(0xffffffffu, p.eff);
@@ -895,6 +982,7 @@ __global__ void __launch_bounds__(256, SOPS_MIN_BLOCKS) sops_chain_kernel(const 
     L.thr = reinterpret_cast<uint16_t*>(base + P.off_thr);
     L.light = reinterpret_cast<uint16_t*>(base + P.off_aux);
     L.tab = reinterpret_cast<uint16_t*>(base + P.off_tab);
+    L.variant = P.variant;
     L.dirtab = s_dirtab;
     for (;;) {
         uint32_t q = 0;
@@ -1032,6 +1120,7 @@ __global__ void __launch_bounds__(32 * W) sops_chain_cta_kernel(const KParams P)
     L.thr = reinterpret_cast<uint16_t*>(smem + P.off_thr);
     L.light = reinterpret_cast<uint16_t*>(smem + P.off_aux);
     L.tab = reinterpret_cast<uint16_t*>(smem + P.off_tab);
+    L.variant = P.variant;
     L.dirtab = s_dirtab;
     for (;;) {
         __syncthreads();                                     // previous instance fully retired (s_q, lattice reusable)
