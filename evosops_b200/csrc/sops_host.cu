@@ -103,6 +103,7 @@ struct Group {                      // one kernel launch: instances of one row-w
     size_t dump_off;                // word offset of this group's dump area
     int wpb, blocks;
     int cta_w;                      // 0: warp-per-instance kernel; else warps per instance of the CTA kernel
+    uint32_t variant;               // AGG commit-round form (KParams::variant)
     size_t smem;
 };
 
@@ -479,7 +480,20 @@ int sops_batch_prepare(sops_ctx* ctx, int behavior, const uint8_t* genomes, uint
                 // 8-warp CTAs that pull instances from a work counter
                 kernel_fn fn = kernel_for(behavior, grp.rw, rng_mode);
                 int wpb = 8;
-                if (grp.count <= 8u * (uint32_t)d.n_sm) wpb = (int)((grp.count + (uint32_t)d.n_sm - 1) / (uint32_t)d.n_sm);
+                bool one_per_scheduler = false;
+                if (grp.count <= 8u * (uint32_t)d.n_sm) {
+                    wpb = (int)((grp.count + (uint32_t)d.n_sm - 1) / (uint32_t)d.n_sm);
+                    if (wpb > 4) {
+                        // A chain is a dependent instruction stream; two chains on one warp scheduler slow each other
+                        // down.  The list is cost-sorted (longest first): if 4 warps per SM — one per scheduler —
+                        // pulling from it finish no later than everything resident at once, run it that way.
+                        double total = 0, longest = 0;
+                        for (uint32_t q : cls[c]) { const double st = (double)steps_of[q % T] + 1.0; total += st; longest = std::max(longest, st); }
+                        const double resident = longest * (1.0 + 0.25 * ((double)wpb / 4.0 - 1.0));
+                        const double pulled = std::max(longest, total / (4.0 * (double)d.n_sm));
+                        if (pulled <= resident) { wpb = 4; one_per_scheduler = true; }
+                    }
+                }
                 if (wpb < 1) wpb = 1;
                 grp.wpb = wpb;
                 grp.smem = smem_per_warp * (size_t)wpb;
@@ -490,6 +504,10 @@ int sops_batch_prepare(sops_ctx* ctx, int behavior, const uint8_t* genomes, uint
                 uint32_t want = (grp.count + (uint32_t)wpb - 1) / (uint32_t)wpb;
                 uint32_t cap = (uint32_t)per_sm * (uint32_t)d.n_sm;
                 grp.blocks = (int)std::min(want, cap);
+                if (one_per_scheduler) grp.blocks = std::min(grp.blocks, d.n_sm);
+                // aggregation commit rounds: the straight-line two-per-round form is built for few, latency-bound
+                // chains; with the machine full, issue slots are the limit and the "touched lanes only" form wins
+                grp.variant = grp.count > 8u * (uint32_t)d.n_sm ? 1u : 0u;
             }
             d.groups.push_back(grp);
         }
@@ -547,7 +565,7 @@ int sops_batch_launch(sops_ctx* ctx) {
             kp.words_per_warp = g.words_per_warp;
             kp.off_p0 = g.off_p0; kp.off_p1 = g.off_p1; kp.off_p2 = g.off_p2;
             kp.off_pos = g.off_pos; kp.off_thr = g.off_thr; kp.off_aux = g.off_aux; kp.off_tab = g.off_tab;
-            { const char* v = getenv("SOPS_AGG_VARIANT"); kp.variant = v ? (uint32_t)atoi(v) : 0u; }
+            { const char* v = getenv("SOPS_AGG_VARIANT"); kp.variant = v ? (uint32_t)atoi(v) : g.variant; }   // env: experiments only
             kp.plane_words = g.plane_words; kp.pos_words = g.pos_words;
             kernel_fn fn = g.cta_w ? kernel_for_cta(ctx->behavior, g.rw) : kernel_for(ctx->behavior, g.rw, ctx->rng_mode);
             cudaStream_t st = d.stream;

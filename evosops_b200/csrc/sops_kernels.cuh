@@ -539,78 +539,94 @@ __device__ __forceinline__ uint32_t resolve_batch_agg(const Lat& L, const Geo& g
         if (VERIFY) A &= lowmask(R);
         low = A & (0u - A);
     };
-    prepare();
-    while (low) {
-        const uint32_t f1 = bfind32(low);
-        if (low & stale) {                                   // warp-uniform, rare: re-read, then it is an ordinary candidate
-            if (lane == f1) { load_proposal<AGG, RW>(L, g, p); prepare(); }
-            stale ^= low;
-            revote();
-            continue;
-        }
-        // second-lowest candidate: committed in the same round when the two moves cannot interact
-        uint32_t low2 = 0;
-        if (PAIR) { const uint32_t rest = A ^ low; low2 = rest & (0u - rest) & ~stale; }
-        const uint32_t f2r = bfind32(low2);                  // 0xffffffff for "none": shuffles then read lane 31, unused
-        uint32_t w0 = 0, w1 = 0;
-        own_cells_load(lane, f1, a_ws, a_wt, w0, w1);
-        const uint32_t sf1 = __shfl_sync(0xffffffffu, p.s, f1);
-        const uint32_t tf1 = __shfl_sync(0xffffffffu, p.tt, f1) & 0xffffu;
-        uint32_t sf2 = 0, tf2 = 0, f2 = 0xffffffffu;
+    // the candidates of the upcoming round: the lowest, and (PAIR) the second-lowest unless it is stale; their moves
+    uint32_t low2 = 0, f1, f2r = 0xffffffffu, sf1, tf1, sf2 = 0, tf2 = 0;
+    auto select = [&]() {
+        f1 = bfind32(low);                                   // 0xffffffff for "none": the shuffles then read lane 31, unused
+        sf1 = __shfl_sync(0xffffffffu, p.s, f1);
+        tf1 = __shfl_sync(0xffffffffu, p.t, f1);
         if (PAIR) {
+            const uint32_t rest = A & (A - 1u);               // A without its lowest bit (when low is 0, A is too)
+            low2 = rest & (0u - rest) & ~stale;
+            f2r = bfind32(low2);
             sf2 = __shfl_sync(0xffffffffu, p.s, f2r);
-            tf2 = __shfl_sync(0xffffffffu, p.tt, f2r) & 0xffffu;
+            tf2 = __shfl_sync(0xffffffffu, p.t, f2r);
+        }
+    };
+    prepare();
+    select();
+    for (;;) {
+        uint32_t dU2 = 0;
+        bool viol = false;
+        // ---- fast rounds: one straight-line body, one branch at the bottom ----
+        while (low & ~stale) {
             // c1 flips cells within distance 1 of sf1; c2 decides from cells within distance 2 of sf2: with the two
             // sources more than 3 apart (Chebyshev) neither move can change the other's decision or particle
-            const uint32_t dd = sf1 - sf2 + 0x0303u;
-            const bool near = ((dd | (dd + 0x0101u)) & 0xFFFFF8F8u) == 0u;
-            if (near) low2 = 0;
-            f2 = low2 ? f2r : 0xffffffffu;
-        }
-        const bool later1 = lane_g > f1, later2 = PAIR && lane_g > f2;
-        uint32_t dU1 = win25_patch(sf1, tf1 - sf1, org);
-        asm volatile("" : "+r"(dU1));                        // keep the patch arithmetic out of a divergent branch
-        dU1 = later1 ? dU1 : 0u;
-        uint32_t dU2 = 0;
-        if (PAIR) {
-            dU2 = win25_patch(sf2, tf2 - sf2, org);
-            asm volatile("" : "+r"(dU2));
-            dU2 = later2 ? dU2 : 0u;
-        }
-        const uint32_t st1 = __ballot_sync(0xffffffffu, later1 && p.s == sf1);   // proposed the moved particle again
-        const uint32_t st2 = PAIR ? __ballot_sync(0xffffffffu, later2 && p.s == sf2) : 0u;
-        p.U0 ^= dU1 ^ dU2;
-        own_cells_store(lane, f1, a_ws, a_wt, a_pos, w0 ^ m_s, w1 ^ m_t, p.t);
-        p.pd = lane == f1 ? 0xffffffffu : p.pd;
-        uint32_t x0 = 0, x1 = 0;
-        if (PAIR) own_cells_load(lane, f2, a_ws, a_wt, x0, x1);   // after c1's stores: the two moves may share a word
-        stale |= st1;
-        ++ncommit;
-        __syncwarp();
-        derive<AGG>(L, g, p);
-        if (VERIFY) {
-            const uint32_t X = __ballot_sync(0xffffffffu, active && p.poss != poss0) & lowmask(R) & ~stale;
-            if (X) R = (uint32_t)__ffs(X) - 1;
-        }
-        const uint32_t E = __ballot_sync(0xffffffffu, p.eff);
-        if (PAIR && low2) {
-            // lanes strictly between the two: they saw c1 only; if one of them is a candidate now it precedes c2
-            const uint32_t between = (low2 - 1u) & ~(low | (low - 1u));
-            if ((E | stale) & between) {                     // rare: undo c2's patch, it is selected again later
-                p.U0 ^= dU2;
-                revote();
-                continue;
+            uint32_t l2 = 0, f2 = 0xffffffffu;
+            if (PAIR) {
+                const uint32_t dd = sf1 - sf2 + 0x0303u;
+                const bool near = ((dd | (dd + 0x0101u)) & 0xFFFFF8F8u) == 0u;
+                l2 = near ? 0u : low2;
+                f2 = l2 ? f2r : 0xffffffffu;
             }
-            own_cells_store(lane, f2, a_ws, a_wt, a_pos, x0 ^ m_s, x1 ^ m_t, p.t);
-            p.pd = lane == f2 ? 0xffffffffu : p.pd;
-            stale |= st2;
-            ++ncommit;
-            A = (E & ~low2) | stale;
-        } else {
-            A = E | stale;
+            // lanes strictly between the two saw c1 only; if one of them is a candidate afterwards it precedes c2
+            const uint32_t between = l2 ? ((l2 - 1u) & ~(low | (low - 1u))) : 0u;
+            const bool later1 = lane_g > f1, later2 = PAIR && lane_g > f2;
+            uint32_t w0 = 0, w1 = 0;
+            own_cells_load(lane, f1, a_ws, a_wt, w0, w1);
+            uint32_t dU1 = win25_patch(sf1, tf1 - sf1, org);
+            asm volatile("" : "+r"(dU1));                    // keep the patch arithmetic out of a divergent branch
+            dU1 = later1 ? dU1 : 0u;
+            if (PAIR) {
+                dU2 = win25_patch(sf2, tf2 - sf2, org);
+                asm volatile("" : "+r"(dU2));
+                dU2 = later2 ? dU2 : 0u;
+            }
+            const uint32_t st1 = __ballot_sync(0xffffffffu, later1 && p.s == sf1);   // proposed the moved particle again
+            const uint32_t st2 = PAIR ? __ballot_sync(0xffffffffu, later2 && p.s == sf2) : 0u;
+            p.U0 ^= dU1 ^ dU2;
+            own_cells_store(lane, f1, a_ws, a_wt, a_pos, w0 ^ m_s, w1 ^ m_t, p.t);
+            p.pd = lane == f1 ? 0xffffffffu : p.pd;
+            uint32_t x0 = 0, x1 = 0;
+            if (PAIR) own_cells_load(lane, f2, a_ws, a_wt, x0, x1);   // after c1's stores: the two moves may share a word
+            stale |= st1;
+            __syncwarp();
+            derive<AGG>(L, g, p);
+            if (VERIFY) {
+                const uint32_t X = __ballot_sync(0xffffffffu, active && p.poss != poss0) & lowmask(R) & ~stale;
+                if (X) R = (uint32_t)__ffs(X) - 1;
+            }
+            const uint32_t E = __ballot_sync(0xffffffffu, p.eff);
+            viol = PAIR && ((E | stale) & between) != 0u;    // rare: c2 has to wait (handled below the loop)
+            const uint32_t f2c = viol ? 0xffffffffu : f2;
+            if (PAIR) {
+                own_cells_store(lane, f2c, a_ws, a_wt, a_pos, x0 ^ m_s, x1 ^ m_t, p.t);
+                p.pd = lane == f2c ? 0xffffffffu : p.pd;
+            }
+#ifdef SOPS_COUNT_ROUNDS                                     // diagnostic build: "committed" counts commit rounds instead
+            ncommit += 1u;
+#else
+            ncommit += 1u + ((PAIR && l2 != 0u && !viol) ? 1u : 0u);
+#endif
+            stale |= viol ? 0u : st2;
+            A = (E & ~l2) | stale;
+            if (VERIFY) A &= lowmask(R);
+            low = viol ? 0u : (A & (0u - A));
+            select();
         }
-        if (VERIFY) A &= lowmask(R);
-        low = A & (0u - A);
+        if (viol) {                                          // undo c2's patch; it is selected again after the re-vote
+            p.U0 ^= dU2;
+            revote();
+            select();
+            continue;
+        }
+        if (!low) break;
+        // the lowest candidate is stale: it re-reads the lattice (everything before it is committed) and is an ordinary
+        // candidate from then on — warp-uniform, rare
+        if (lane == f1) { load_proposal<AGG, RW>(L, g, p); prepare(); }
+        stale ^= low;
+        revote();
+        select();
     }
     return R;
 }
@@ -961,11 +977,14 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
     __syncwarp();
 }
 
+// AGG: 3 CTAs of 256 threads per SM = 80 registers per thread (the allocation granule makes 81..88 cost a whole CTA
+// of occupancy on the seed sweeps).  The other behaviours measured 4-5 % slower under the same cap on their GA
+// batches and keep ptxas' own choice.
 #ifndef SOPS_MIN_BLOCKS
 #define SOPS_MIN_BLOCKS 1
 #endif
 template <int BEH, int RW, int MODE>
-__global__ void __launch_bounds__(256, SOPS_MIN_BLOCKS) sops_chain_kernel(const KParams P) {
+__global__ void __launch_bounds__(256, BEH == AGG ? 3 : SOPS_MIN_BLOCKS) sops_chain_kernel(const KParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint4 s_dirtab[8];
     if (threadIdx.x == 0) {

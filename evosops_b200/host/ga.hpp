@@ -194,10 +194,12 @@ public:
             std::vector<uint8_t> orient;
             if (spec_.behavior == Loco) { orient.resize(todo.size() * T); for (auto& o : orient) o = (uint8_t)rng_.inclusive(1, 3); }   // locomotion.rs:109
             std::vector<sops_result> out;
-            // kernel hint (ours): late generations accept < 1 % of attempts; there the 4-warp-per-chain kernel
-            // is ~1.3x faster.  Results do not depend on the choice.
+            // kernel hint (ours): when a generation accepts < 1 % of its attempts the 4-warp-per-chain kernel can be
+            // faster.  Not for aggregation: its warp kernel (hashed decision, one chain per warp scheduler) measured
+            // faster than the CTA form on late-generation populations too.  Results do not depend on the choice.
+            const bool use_cta = low_acceptance_ && spec_.behavior != Agg;
             ev_.eval(spec_.behavior, flat, (uint32_t)todo.size(), trials, granularity_, w1_, w2_, ms, orient, 0,
-                     low_acceptance_ ? (uint32_t)SOPS_F_FORCE_CTA : 0u, out);
+                     use_cta ? (uint32_t)SOPS_F_FORCE_CTA : 0u, out);
             uint64_t cnt[6];
             ev_.counters(cnt);
             if (cnt[0] > 0) low_acceptance_ = (double)cnt[2] / (double)cnt[0] < 0.01;
@@ -255,7 +257,7 @@ public:
             if (verbose_)                                                          // extension (-v): the reference only has whole seconds
                 std::fprintf(log_, "Generation Wall Time: %.3fs  Evaluated Instances: %llu  Kernel: %s\n",
                              std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(),
-                             (unsigned long long)evaluated_, low_acceptance_ ? "cta" : "warp");
+                             (unsigned long long)evaluated_, (low_acceptance_ && spec_.behavior != Agg) ? "cta" : "warp");
             std::fflush(log_);
         }
     }
