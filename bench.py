@@ -350,7 +350,7 @@ def main():
                              "alg_bytes_per_attempt": alg_bytes, "p_poss": p_poss, "p_acc": p_acc,
                              "peak_source": "%s sm_max_mhz x 148 SMs x 128 B/clk shared memory" % peak_src,
                              "issue": issue_view(attempts_step / (k_ms * 1e-3), p_poss, sm_mhz),
-                             "note": "750 chains on 9472 warp slots: dependent-latency bound, the slowest genome's chains set the time; see DESIGN.md"},
+                             "note": "750 chains pulled by 592 warps (one per warp scheduler): dependent-latency bound, the slowest genome's chains set the time; see DESIGN.md"},
                 "mean_fitness": mean_fitness}
         if sweep_local:
             ms_s, pp_s, pa_s, att_s = sweep_local
