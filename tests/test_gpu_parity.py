@@ -121,6 +121,32 @@ def test_agg_many_seeds_short_chains(ctx, genomes, rng_mode, kflag):
     check_equal(ctx, E.AGG, gs, sizes, seeds, got, want, cnt, rng_mode, 300000, move_seeds=ms, dump_every=3, flags=kflag)
 
 
+@pytest.mark.parametrize("variant", ["0", "1"], ids=["straight-line", "touched-only"])
+@pytest.mark.parametrize("rng_mode", [E.RNG_VERIFY, E.RNG_FAST])
+def test_agg_commit_rounds_under_heavy_acceptance(ctx, genomes, rng_mode, variant, monkeypatch):
+    # genomes that accept (almost) every possible move: many candidates per 32-step batch, so the commit rounds run
+    # their rare paths all the time — two commits per round, a candidate turning up between the pair (undo), lanes
+    # that proposed the particle that just moved (stale, re-read).  Both commit-round forms, RW 1 and 2.
+    monkeypatch.setenv("SOPS_AGG_VARIANT", variant)          # read by the library at launch time (experiments knob)
+    rng = np.random.default_rng(7)
+    gs = np.stack([np.zeros(48, dtype=np.uint8), np.ones(48, dtype=np.uint8),
+                   rng.integers(0, 3, size=48, dtype=np.uint8), genomes["agg_random"]])
+    sizes = [(6, 3), (6, 1), (10, 7), (13, 9), (20, 14), (9, 2)]
+    seeds = [3, 4, 5, 6, 7, 8]
+    got, want, cnt = run_pair(ctx, E.AGG, gs, sizes, seeds, rng_mode, steps=120001)
+    check_equal(ctx, E.AGG, gs, sizes, seeds, got, want, cnt, rng_mode, 120001)
+    assert cnt[2] > 0.1 * cnt[0]                              # the batch really is acceptance-heavy
+
+
+def test_agg_large_batch_takes_the_throughput_form(ctx, genomes):
+    # more chains than 8 per SM: the host picks the "touched lanes only" rounds and 8-warp CTAs; same bits
+    gs = np.stack([np.zeros(48, dtype=np.uint8), genomes["agg_evolved"]])
+    seeds = list(range(1, 1201))
+    sizes = [(6, 3)] * len(seeds)
+    got, want, cnt = run_pair(ctx, E.AGG, gs, sizes, seeds, E.RNG_FAST, steps=20000)
+    check_equal(ctx, E.AGG, gs, sizes, seeds, got, want, cnt, E.RNG_FAST, 20000, dump_every=97)
+
+
 @pytest.mark.parametrize("rng_mode", [E.RNG_VERIFY, E.RNG_FAST])
 def test_sep_chains_bit_exact(ctx, genomes, rng_mode, kflag):
     _skip_redundant(rng_mode, kflag)
