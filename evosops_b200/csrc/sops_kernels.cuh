@@ -506,7 +506,7 @@ __device__ __forceinline__ void own_cells_store(uint32_t lane, uint32_t f, uint3
         :: "r"(lane), "r"(f), "r"(a_ws), "r"(v0), "r"(a_wt), "r"(v1), "r"(a_pos), "h"((uint16_t)t) : "memory");
 }
 
-template <int RW, bool VERIFY>
+template <int BEH, int RW, bool VERIFY>
 __device__ __forceinline__ uint32_t resolve_batch_agg(const Lat& L, const Geo& g, uint32_t lane, bool active, Prop& p, uint32_t& ncommit) {
     constexpr bool PAIR = !VERIFY;                           // commit two candidates per round when they cannot interact
     uint32_t R = 32;
@@ -530,7 +530,7 @@ __device__ __forceinline__ uint32_t resolve_batch_agg(const Lat& L, const Geo& g
     };
     auto revote = [&]() {
         __syncwarp();
-        derive<AGG>(L, g, p);
+        derive<BEH>(L, g, p);
         if (VERIFY) {
             const uint32_t X = __ballot_sync(0xffffffffu, active && p.poss != poss0) & lowmask(R) & ~stale;
             if (X) R = (uint32_t)__ffs(X) - 1;
@@ -591,7 +591,7 @@ __device__ __forceinline__ uint32_t resolve_batch_agg(const Lat& L, const Geo& g
             if (PAIR) own_cells_load(lane, f2, a_ws, a_wt, x0, x1);   // after c1's stores: the two moves may share a word
             stale |= st1;
             __syncwarp();
-            derive<AGG>(L, g, p);
+            derive<BEH>(L, g, p);
             if (VERIFY) {
                 const uint32_t X = __ballot_sync(0xffffffffu, active && p.poss != poss0) & lowmask(R) & ~stale;
                 if (X) R = (uint32_t)__ffs(X) - 1;
@@ -623,7 +623,7 @@ __device__ __forceinline__ uint32_t resolve_batch_agg(const Lat& L, const Geo& g
         if (!low) break;
         // the lowest candidate is stale: it re-reads the lattice (everything before it is committed) and is an ordinary
         // candidate from then on — warp-uniform, rare
-        if (lane == f1) { load_proposal<AGG, RW>(L, g, p); prepare(); }
+        if (lane == f1) { load_proposal<BEH, RW>(L, g, p); prepare(); }
         stale ^= low;
         revote();
         select();
@@ -637,7 +637,10 @@ __device__ __forceinline__ uint32_t resolve_batch_agg(const Lat& L, const Geo& g
 // the batch is cut at that lane (returned bound R; lanes >= R are not retired).  ncommit is warp-uniform.
 template <int BEH, int RW, bool VERIFY>
 __device__ __forceinline__ uint32_t resolve_batch(const Lat& L, const Geo& g, uint32_t lane, bool active, Prop& p, uint32_t& ncommit) {
-    if (BEH == AGG && L.variant == 0) return resolve_batch_agg<RW, VERIFY>(L, g, lane, active, p, ncommit);
+    // (COAT commits the same way and runs bit-exact through resolve_batch_agg<COAT> too, but its decision — six POPCs and
+    // three table steps — is too dear to repeat in every lane after every commit: measured +5 % at p_acc 0.5, -20 % at
+    // p_acc 0.02, so only aggregation is dispatched there.)
+    if (BEH == AGG && L.variant == 0) return resolve_batch_agg<BEH, RW, VERIFY>(L, g, lane, active, p, ncommit);
     uint32_t R = 32;
     for (;;) {
         uint32_t A = __ballot_sync(0xffffffffu, p.eff);
