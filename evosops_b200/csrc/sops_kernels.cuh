@@ -513,9 +513,9 @@ __device__ __forceinline__ uint32_t resolve_batch_agg(const Lat& L, const Geo& g
     uint32_t stale = 0;                                      // warp-uniform lane mask
     // VERIFY: a lane below the cut R still has the possible-ness it was aligned with (a flip cuts the batch there)
     const bool poss0 = p.poss;
+    if (!__any_sync(0xffffffffu, p.eff)) return R;           // most batches of a low-acceptance chain end here
     uint32_t A = __ballot_sync(0xffffffffu, p.eff);
     uint32_t low = A & (0u - A);                             // lowest candidate as a one-hot mask (0: none)
-    if (!low) return R;
     const uint32_t lane_g = active ? lane : 0u;              // an inactive lane is never "later than f": never patched, never stale
     // this lane's own commit, prepared once: word addresses and bit masks of its two cells, its position slot
     uint32_t a_ws, a_wt, m_s, m_t, org;
@@ -614,13 +614,13 @@ __device__ __forceinline__ uint32_t resolve_batch_agg(const Lat& L, const Geo& g
             low = viol ? 0u : (A & (0u - A));
             select();
         }
+        if (!low && !viol) break;                            // the common exit: one test
         if (viol) {                                          // undo c2's patch; it is selected again after the re-vote
             p.U0 ^= dU2;
             revote();
             select();
             continue;
         }
-        if (!low) break;
         // the lowest candidate is stale: it re-reads the lattice (everything before it is committed) and is an ordinary
         // candidate from then on — warp-uniform, rare
         if (lane == f1) { load_proposal<BEH, RW>(L, g, p); prepare(); }
