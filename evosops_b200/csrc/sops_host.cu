@@ -495,6 +495,7 @@ int sops_batch_prepare(sops_ctx* ctx, int behavior, const uint8_t* genomes, uint
                     }
                 }
                 if (wpb < 1) wpb = 1;
+                while (wpb > 1 && smem_per_warp * (size_t)wpb + 1024 > 227u * 1024u) wpb /= 2;   // largest arenas: fewer warps per CTA
                 grp.wpb = wpb;
                 grp.smem = smem_per_warp * (size_t)wpb;
                 if (grp.smem + 1024 > 48 * 1024)                   // + the kernels' static shared memory
