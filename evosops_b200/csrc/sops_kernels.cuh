@@ -185,7 +185,7 @@ __device__ __forceinline__ uint32_t win25(const uint32_t* p, uint32_t r, uint32_
 }
 // XOR mask of the two flipped cells x and x + delta (a committed move) in the 5x5 window whose top-left
 // cell is `org` (= centre - 0x0202).  Cells outside the window contribute 0.
-__device__ __forceinline__ uint32_t win25_patch(uint32_t x, uint32_t delta, uint32_t org) {
+__host__ __device__ __forceinline__ uint32_t win25_patch(uint32_t x, uint32_t delta, uint32_t org) {
     const uint32_t v = x - org;                              // (dr + 2) | (dc + 2) << 8 when inside
     const uint32_t w = v + delta;
     const bool vin = ((v | (v + 0x0303u)) & 0xFFFFF8F8u) == 0u;   // both fields in 0..4 (a borrow sets high bits)
@@ -193,6 +193,14 @@ __device__ __forceinline__ uint32_t win25_patch(uint32_t x, uint32_t delta, uint
     const uint32_t iv = (v & 7u) * (uint32_t)WS + (v >> 8), iw = (w & 7u) * (uint32_t)WS + (w >> 8);
     const uint32_t mv = 1u << (iv & 31u), mw = 1u << (iw & 31u);
     return (vin ? mv : 0u) ^ (win_ ? mw : 0u);
+}
+
+// Two packed cells (row | col << 8) within Chebyshev distance 3 of each other?  Never misses a near pair; the byte
+// arithmetic can wrap for row distances >= 250 (largest arenas only) and then answers "near", the safe side.  Two moves whose SOURCES are farther apart than that cannot interact:
+// a move flips cells within distance 1 of its source, a decision reads cells within distance 2 of its source.
+__host__ __device__ __forceinline__ bool near_sources(uint32_t a, uint32_t b) {
+    const uint32_t dd = a - b + 0x0303u;                     // fields 0..6 when |drow|, |dcol| <= 3
+    return ((dd | (dd + 0x0101u)) & 0xFFFFF8F8u) == 0u;
 }
 
 // group index tables --------------------------------------------------------------------------------
@@ -564,9 +572,7 @@ __device__ __forceinline__ uint32_t resolve_batch_agg(const Lat& L, const Geo& g
             // sources more than 3 apart (Chebyshev) neither move can change the other's decision or particle
             uint32_t l2 = 0, f2 = 0xffffffffu;
             if (PAIR) {
-                const uint32_t dd = sf1 - sf2 + 0x0303u;
-                const bool near = ((dd | (dd + 0x0101u)) & 0xFFFFF8F8u) == 0u;
-                l2 = near ? 0u : low2;
+                l2 = near_sources(sf1, sf2) ? 0u : low2;
                 f2 = l2 ? f2r : 0xffffffffu;
             }
             // lanes strictly between the two saw c1 only; if one of them is a candidate afterwards it precedes c2

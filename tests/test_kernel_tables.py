@@ -1,0 +1,93 @@
+"""CPU check of the kernel header's compile-time tables (window masks, target bit, hash multipliers) against a
+from-scratch restatement of the reference's lattice geometry (mod.rs:80-82 directions, mod.rs:186-232 back / mid /
+front neighbourhoods).  The tool is host code compiled by nvcc; nothing runs on a GPU."""
+import json
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DIRS = [(-1, 0), (1, 0), (0, -1), (0, 1), (-1, -1), (1, 1)]          # mod.rs:80-82, (row, col) steps
+
+
+@pytest.fixture(scope="module")
+def tables(tmp_path_factory):
+    from evosops_b200 import _build
+    exe = str(tmp_path_factory.mktemp("tables") / "dump_tables")
+    subprocess.check_call([_build.nvcc_path(), "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "tools", "dump_tables.cu")])
+    return json.loads(subprocess.check_output([exe], text=True))
+
+
+def nbrs(cell):
+    return {(cell[0] + dr, cell[1] + dc) for dr, dc in DIRS}
+
+
+def test_window_masks_follow_the_lattice_geometry(tables):
+    ws = tables["ws"]
+    assert ws >= 5 and 5 * ws <= 32                           # five rows of five cells fit a 32-bit window
+
+    def bit(cell):                                            # window centred on the source (0, 0): bit = ws*(r+2) + (c+2)
+        assert -2 <= cell[0] <= 2 and -2 <= cell[1] <= 2
+        return 1 << (ws * (cell[0] + 2) + (cell[1] + 2))
+
+    for d, (dr, dc) in enumerate(DIRS):
+        t = tables["dirs"][d]
+        s, tgt = (0, 0), (dr, dc)
+        mid = nbrs(s) & nbrs(tgt)                             # common neighbours
+        back = nbrs(s) - mid - {tgt}
+        front = nbrs(tgt) - mid - {s}
+        assert (len(back), len(mid), len(front)) == (3, 2, 3)  # phenotype [4][3][4] (mod.rs:25-36)
+        assert (t["dr"], t["dc"]) == (dr, dc)
+        assert t["delta"] == dr + 256 * dc                    # packed (row | col << 8) step
+        assert 1 << t["tbit"] == bit(tgt)
+        assert t["back"] == sum(bit(c) for c in back)
+        assert t["mid"] == sum(bit(c) for c in mid)
+        assert t["front"] == sum(bit(c) for c in front)
+        assert t["all"] == t["back"] | t["mid"] | t["front"]
+
+
+def test_window_hash_is_a_bijection_per_direction(tables):
+    for t in tables["dirs"]:
+        cells = [1 << k for k in range(32) if (t["all"] >> k) & 1]
+        assert len(cells) == 8
+        seen = set()
+        for pattern in range(256):
+            x = sum(c for k, c in enumerate(cells) if (pattern >> k) & 1)
+            seen.add(((x * t["magic"]) & 0xFFFFFFFF) >> 24)
+        assert seen == set(range(256))
+
+
+def test_window_patch_flips_exactly_the_cells_inside_the_window(tables):
+    # a committed move flips its source and target cell; a lane's 5x5 window must change in exactly those of the two
+    # cells that lie inside it — for every relative position and direction
+    ws = tables["ws"]
+    assert len(tables["patch"]) == 21 * 21 * 6               # offsets -9..9 plus far ones (borrows of the packed subtraction)
+    for orow, ocol, d, mask in tables["patch"]:
+        want = 0
+        for cell in ((orow, ocol), (orow + DIRS[d][0], ocol + DIRS[d][1])):
+            if -2 <= cell[0] <= 2 and -2 <= cell[1] <= 2:
+                want ^= 1 << (ws * (cell[0] + 2) + (cell[1] + 2))
+        assert mask == want, (orow, ocol, d, mask, want)
+
+
+def test_pair_commit_criterion(tables):
+    # (1) the packed-arithmetic test never misses a near pair (that would be a wrong result); it is exactly
+    # "Chebyshev distance <= 3" except for row distances >= 250, where the byte arithmetic wraps and it errs on the
+    # safe side (claims "near": the two moves are then simply committed one after the other)
+    assert len(tables["near"]) == 17 ** 4
+    for r1, c1, r2, c2, near in tables["near"]:
+        truly = max(abs(r1 - r2), abs(c1 - c2)) <= 3
+        if truly:
+            assert near == 1, (r1, c1, r2, c2)
+        elif abs(r1 - r2) < 250:
+            assert near == 0, (r1, c1, r2, c2)
+    # (2) and beyond that distance two moves cannot interact: a move flips its source and a cell next to it, a
+    # decision (and the "same particle" test) reads only the 5x5 window around its own source
+    for orow in range(-6, 7):
+        for ocol in range(-6, 7):
+            if max(abs(orow), abs(ocol)) <= 3:
+                continue
+            for dr, dc in DIRS:
+                for cell in ((orow, ocol), (orow + dr, ocol + dc)):      # the other move's two cells, relative to my source
+                    assert max(abs(cell[0]), abs(cell[1])) > 2

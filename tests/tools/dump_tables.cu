@@ -1,0 +1,37 @@
+// Test tool (CPU): prints the kernel header's compile-time direction tables so tests/test_kernel_tables.py can
+// check them against a from-scratch restatement of the lattice geometry.  Host code only — no CUDA calls.
+#include <cstdio>
+#include "../../evosops_b200/csrc/sops_kernels.cuh"
+
+int main() {
+    using namespace sops;
+    std::printf("{\"ws\": %d, \"dirs\": [", WS);
+    for (int d = 0; d < 6; ++d) {
+        std::printf("%s{\"dr\": %d, \"dc\": %d, \"delta\": %d, \"tbit\": %u, \"back\": %u, \"mid\": %u, \"front\": %u, \"all\": %u, \"magic\": %u}",
+                    d ? ", " : "", dir_dr(d), dir_dc(d), dir_delta(d), dir_tbit(d), dir_back5(d), dir_mid5(d), dir_front5(d),
+                    dir_all5(d), dir_magic(d));
+    }
+    std::printf("], \"patch\": [");
+    // win25_patch over every (source offset, direction) around a window whose centre is the padded cell (40, 50)
+    const uint32_t centre = 40u | (50u << 8), org = centre - 0x0202u;
+    bool first = true;
+    for (int orow = -38; orow <= 38; orow += (orow >= -9 && orow < 9) ? 1 : 29)
+        for (int ocol = -48; ocol <= 48; ocol += (ocol >= -9 && ocol < 9) ? 1 : 39)
+            for (int d = 0; d < 6; ++d) {
+                const uint32_t sf = (uint32_t)(40 + orow) | ((uint32_t)(50 + ocol) << 8);
+                const uint32_t tf = (sf + (uint32_t)dir_delta(d)) & 0xffffu;
+                std::printf("%s[%d, %d, %d, %u]", first ? "" : ", ", orow, ocol, d, win25_patch(sf, tf - sf, org));
+                first = false;
+            }
+    std::printf("], \"near\": [");
+    // near_sources over a grid of padded cells incl. the extremes of the u8 coordinate range
+    const int probe[] = {2, 3, 5, 6, 7, 9, 10, 40, 41, 43, 44, 45, 128, 250, 253, 254, 255};
+    first = true;
+    for (int r1 : probe) for (int c1 : probe) for (int r2 : probe) for (int c2 : probe) {
+        const uint32_t a = (uint32_t)r1 | ((uint32_t)c1 << 8), b = (uint32_t)r2 | ((uint32_t)c2 << 8);
+        std::printf("%s[%d, %d, %d, %d, %d]", first ? "" : ", ", r1, c1, r2, c2, near_sources(a, b) ? 1 : 0);
+        first = false;
+    }
+    std::printf("]}\n");
+    return 0;
+}
