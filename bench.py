@@ -197,6 +197,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"              # keep NCCL's version banner out of stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
