@@ -326,7 +326,8 @@ __device__ __forceinline__ void derive(const Lat& L, const Geo& g, Prop& p) {
         if (p.kind == 2) thr = min(thr, thr2);               // max gene == min probability (tables are non-increasing)
         // a same-colour swap draws and is accepted but nothing moves (separation.rs:287-288)
         p.eff = p.poss && p.pd < thr && !(p.kind == 2 && col2 == col);
-        p.tt = (p.tt & 0x0fffffffu) | ((col ^ col2) << 28);     // a move flips col (col2 == 0), a swap col ^ col2
+        // a move flips col (col2 == 0), a swap col ^ col2; bit 31 says "swap" to the lanes the move is broadcast to
+        p.tt = (p.tt & 0x0fffffffu) | ((col ^ col2) << 28) | (p.kind == 2 ? 0x80000000u : 0u);
     }
 }
 
@@ -392,6 +393,21 @@ __device__ __forceinline__ void flip_pair(uint32_t* plane, uint32_t sr, uint32_t
     }
 }
 
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// one lane (on != 0) flips one bit in each of two shared-memory words
+__device__ __forceinline__ void own_flip(bool on, uint32_t a0, uint32_t a1, uint32_t m0, uint32_t m1) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t.reg .b32 u, v;\n\t"
+        "setp.ne.u32 q, %0, 0;\n\t"
+        "@q ld.shared.b32 u, [%1];\n\t"
+        "@q ld.shared.b32 v, [%2];\n\t"
+        "@q xor.b32 u, u, %3;\n\t"
+        "@q xor.b32 v, v, %4;\n\t"
+        "@q st.shared.b32 [%1], u;\n\t"
+        "@q st.shared.b32 [%2], v;\n\t}"
+        :: "r"((uint32_t)on), "r"(a0), "r"(a1), "r"(m0), "r"(m1) : "memory");
+}
+
 // --- commit of lane f's accepted proposal + incremental repair of every later lane --------------------
 // Lane f flips its two cells (fire-and-forget shared reductions) and rewrites its position.  Every lane then
 // patches its register window with the flipped cells; a lane whose window really changed re-derives, a
@@ -406,11 +422,10 @@ __device__ __forceinline__ void commit_and_repair(const Lat& L, const Geo& g, ui
     const bool mine = lane == f;
     if (BEH == SEP) {
         // colour bits flipped at both cells: a move carries the mover's colour, a swap exchanges two colours
-        const uint32_t kindf = __shfl_sync(0xffffffffu, p.kind, f);
-        const uint32_t idxf = __shfl_sync(0xffffffffu, p.idx, f);
-        x = ttf >> 28;
+        x = (ttf >> 28) & 3u;
+        const bool swap = (ttf >> 31) != 0u;                 // warp-uniform (broadcast)
         uint32_t partner = 0xffffffffu;
-        if (kindf == 2) {
+        if (swap) {
             // the partner's index: the reference's participants.iter().position scan (separation.rs:302),
             // here a warp-wide scan of the position list
             // (every lane scans its strided share with independent loads, one warp reduction at the end)
@@ -419,12 +434,19 @@ __device__ __forceinline__ void commit_and_repair(const Lat& L, const Geo& g, ui
             for (uint32_t i = lane; i < g.n; i += 32) if (L.pos[i] == tf) found = i;
             partner = __reduce_min_sync(0xffffffffu, found);
         }
-        // every operand below is warp-uniform (broadcast, or the result of the scan): all lanes perform the
-        // same stores — no divergent region
-        flip_pair<RW>(L.p0, sfr, sfc, tfr, tfc, (x & 1u) != 0u);
-        flip_pair<RW>(L.p1, sfr, sfc, tfr, tfc, (x & 2u) != 0u);
-        L.pos[idxf] = (uint16_t)tf;
-        if (kindf == 2) L.pos[partner] = (uint16_t)sf;
+        // the committing lane updates the two colour planes itself, from its OWN source / target (predicated loads
+        // and stores: no broadcast-derived address arithmetic, no "which plane" / "same word" branches)
+        {
+            const uint32_t osr = p.s & 0xff, osc = p.s >> 8, otr = p.t & 0xff, otc = p.t >> 8;
+            const uint32_t a_ws = smem_addr(Plane<RW>::word(L.p0, osr, osc)), a_wt = smem_addr(Plane<RW>::word(L.p0, otr, otc));
+            const uint32_t plane1 = smem_addr(L.p1) - smem_addr(L.p0);
+            uint32_t m_s = 1u << (osc & 31u), m_t = 1u << (otc & 31u);
+            if (a_ws == a_wt) m_s = m_t = m_s ^ m_t;         // both cells in one word: the two stores write the same value
+            own_flip(mine && (x & 1u), a_ws, a_wt, m_s, m_t);
+            own_flip(mine && (x & 2u), a_ws + plane1, a_wt + plane1, m_s, m_t);
+        }
+        if (mine) L.pos[p.idx] = (uint16_t)tf;
+        if (swap) L.pos[partner] = (uint16_t)sf;
     } else {
         if (BEH == LOCO) {                                   // locomotion.rs:344-519, net effect
             const uint32_t auxf = __shfl_sync(0xffffffffu, p.aux, f);
@@ -492,8 +514,6 @@ __device__ __forceinline__ void commit_and_repair(const Lat& L, const Geo& g, ui
 //     OWN proposal — nothing is recomputed from the broadcast move, the loads are issued before the broadcast returns;
 //   * the lowest candidate of the next round is selected (one find-leading-one on the isolated lowest bit) and its
 //     move broadcast before the loop branch, so the vote -> branch latency hides behind them.
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
 // the committing lane's own lattice update, in two halves so the loads can be issued early
 __device__ __forceinline__ void own_cells_load(uint32_t lane, uint32_t f, uint32_t a_ws, uint32_t a_wt, uint32_t& w0, uint32_t& w1) {
     asm volatile(
