@@ -377,23 +377,27 @@ __device__ __forceinline__ bool probe_possible(const Lat& L, uint32_t idx, uint3
     return !(Plane<RW>::bit(L.p1, tr, tc) | Plane<RW>::bit(L.p0, tr, tc));
 }
 
-// warp-uniform flip of two cells of one plane (all lanes: same addresses, same values); `on` is uniform too
-template <int RW>
-__device__ __forceinline__ void flip_pair(uint32_t* plane, uint32_t sr, uint32_t sc, uint32_t tr, uint32_t tc, bool on) {
-    if (!on) return;
-    uint32_t* ws = const_cast<uint32_t*>(Plane<RW>::word(plane, sr, sc));
-    uint32_t* wt = const_cast<uint32_t*>(Plane<RW>::word(plane, tr, tc));
-    const uint32_t ms = 1u << (sc & 31u), mt = 1u << (tc & 31u);
-    if (ws == wt) {
-        *ws ^= ms ^ mt;
-    } else {
-        const uint32_t a = *ws, b = *wt;
-        *ws = a ^ ms;
-        *wt = b ^ mt;
-    }
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// the committing lane's own lattice update, in two halves so the loads can be issued early
+__device__ __forceinline__ void own_cells_load(uint32_t lane, uint32_t f, uint32_t a_ws, uint32_t a_wt, uint32_t& w0, uint32_t& w1) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.eq.u32 q, %2, %3;\n\t"
+        "@q ld.shared.b32 %0, [%4];\n\t"
+        "@q ld.shared.b32 %1, [%5];\n\t}"
+        : "+r"(w0), "+r"(w1) : "r"(lane), "r"(f), "r"(a_ws), "r"(a_wt) : "memory");
+}
+__device__ __forceinline__ void own_cells_store(uint32_t lane, uint32_t f, uint32_t a_ws, uint32_t a_wt, uint32_t a_pos,
+                                                uint32_t v0, uint32_t v1, uint32_t t) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.eq.u32 q, %0, %1;\n\t"
+        "@q st.shared.b32 [%2], %3;\n\t"
+        "@q st.shared.b32 [%4], %5;\n\t"
+        "@q st.shared.u16 [%6], %7;\n\t}"
+        :: "r"(lane), "r"(f), "r"(a_ws), "r"(v0), "r"(a_wt), "r"(v1), "r"(a_pos), "h"((uint16_t)t) : "memory");
 }
 
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 // one lane (on != 0) flips one bit in each of two shared-memory words
 __device__ __forceinline__ void own_flip(bool on, uint32_t a0, uint32_t a1, uint32_t m0, uint32_t m1) {
     asm volatile(
@@ -456,14 +460,23 @@ __device__ __forceinline__ void commit_and_repair(const Lat& L, const Geo& g, ui
             if (b2) L.light[b2 - 1] = (uint16_t)((tfr - 2) | ((tfc - 2) << 8));
             wrote = b1 | (b2 << 8);
         }
+        if (BEH != LOCO) {
+            // AGG / COAT lattice update by the committing lane itself, from its OWN source / target: predicated loads and
+            // stores, no "same word" branch (coating generation -13 %; locomotion measured 1-3 % slower this way and
+            // keeps the warp-uniform form below)
+            const uint32_t osr = p.s & 0xff, osc = p.s >> 8, otr = p.t & 0xff, otc = p.t >> 8;
+            const uint32_t a_ws = smem_addr(Plane<RW>::word(L.p0, osr, osc)), a_wt = smem_addr(Plane<RW>::word(L.p0, otr, otc));
+            uint32_t m_s = 1u << (osc & 31u), m_t = 1u << (otc & 31u);
+            if (a_ws == a_wt) m_s = m_t = m_s ^ m_t;         // both cells in one word: the two stores write the same value
+            own_flip(mine, a_ws, a_wt, m_s, m_t);
+        }
     }
-    // AGG / COAT / LOCO lattice update: sf and tf were broadcast, so the two lattice words, their masks and the
-    // new values are warp-uniform.  Every lane performs the same read-modify-write (same address, same value:
-    // one wavefront, no divergence, no atomics): the loads are issued here, the stores after the window patch
-    // below, so the shared-memory latency hides behind that arithmetic.
+    // LOCO lattice update: sf and tf were broadcast, so the two lattice words, their masks and the new values are
+    // warp-uniform.  Every lane performs the same read-modify-write (same address, same value: one wavefront, no
+    // divergence, no atomics): the loads are issued here, the stores after the window patch below.
     uint32_t* ws = nullptr; uint32_t* wt = nullptr;
     uint32_t wa = 0, wb = 0;
-    if (BEH != SEP) {
+    if (BEH == LOCO) {
         ws = const_cast<uint32_t*>(Plane<RW>::word(L.p0, sfr, sfc));
         wt = const_cast<uint32_t*>(Plane<RW>::word(L.p0, tfr, tfc));
         wa = *ws; wb = *wt;
@@ -483,12 +496,14 @@ __device__ __forceinline__ void commit_and_repair(const Lat& L, const Geo& g, ui
             const uint32_t bs = (p.aux >> 8) & 0xff, bt = (p.aux >> 16) & 0xff;
             reread |= (b1 && (bs == b1 || bt == b1)) || (b2 && (bs == b2 || bt == b2));
         }
-        const uint32_t ms = 1u << (sfc & 31u), mt = 1u << (tfc & 31u);
-        if (ws == wt) {                                      // warp-uniform: both cells in one word
-            *ws = wa ^ ms ^ mt;
-        } else {
-            *ws = wa ^ ms;
-            *wt = wb ^ mt;
+        if (BEH == LOCO) {
+            const uint32_t ms = 1u << (sfc & 31u), mt = 1u << (tfc & 31u);
+            if (ws == wt) {                                  // warp-uniform: both cells in one word
+                *ws = wa ^ ms ^ mt;
+            } else {
+                *ws = wa ^ ms;
+                *wt = wb ^ mt;
+            }
         }
         if (mine) L.pos[p.idx] = (uint16_t)tf;
         __syncwarp();
@@ -514,26 +529,6 @@ __device__ __forceinline__ void commit_and_repair(const Lat& L, const Geo& g, ui
 //     OWN proposal — nothing is recomputed from the broadcast move, the loads are issued before the broadcast returns;
 //   * the lowest candidate of the next round is selected (one find-leading-one on the isolated lowest bit) and its
 //     move broadcast before the loop branch, so the vote -> branch latency hides behind them.
-// the committing lane's own lattice update, in two halves so the loads can be issued early
-__device__ __forceinline__ void own_cells_load(uint32_t lane, uint32_t f, uint32_t a_ws, uint32_t a_wt, uint32_t& w0, uint32_t& w1) {
-    asm volatile(
-        "{\n\t.reg .pred q;\n\t"
-        "setp.eq.u32 q, %2, %3;\n\t"
-        "@q ld.shared.b32 %0, [%4];\n\t"
-        "@q ld.shared.b32 %1, [%5];\n\t}"
-        : "+r"(w0), "+r"(w1) : "r"(lane), "r"(f), "r"(a_ws), "r"(a_wt) : "memory");
-}
-__device__ __forceinline__ void own_cells_store(uint32_t lane, uint32_t f, uint32_t a_ws, uint32_t a_wt, uint32_t a_pos,
-                                                uint32_t v0, uint32_t v1, uint32_t t) {
-    asm volatile(
-        "{\n\t.reg .pred q;\n\t"
-        "setp.eq.u32 q, %0, %1;\n\t"
-        "@q st.shared.b32 [%2], %3;\n\t"
-        "@q st.shared.b32 [%4], %5;\n\t"
-        "@q st.shared.u16 [%6], %7;\n\t}"
-        :: "r"(lane), "r"(f), "r"(a_ws), "r"(v0), "r"(a_wt), "r"(v1), "r"(a_pos), "h"((uint16_t)t) : "memory");
-}
-
 template <int BEH, int RW, bool VERIFY>
 __device__ __forceinline__ uint32_t resolve_batch_agg(const Lat& L, const Geo& g, uint32_t lane, bool active, Prop& p, uint32_t& ncommit) {
     constexpr bool PAIR = !VERIFY;                           // commit two candidates per round when they cannot interact
