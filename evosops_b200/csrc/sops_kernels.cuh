@@ -7,18 +7,20 @@
 //   locomotion   src/SOPSCore/locomotion.rs:98-255, 260-290, 344-532, 551-654, 661-706
 //
 // Design:
-//   * The lattice lives in shared memory as bit planes (one 32- or 64-bit word per padded row), the
-//     particle list as packed u16 (row+1 | (col+1) << 8), the genome as u16 acceptance thresholds.
+//   * The lattice lives in shared memory as bit planes (1, 2, 4 or 8 32-bit words per row of the grid padded by two
+//     cells per side), the particle list as packed u16 (row+2 | (col+2) << 8), the genome as u16 acceptance thresholds.
 //   * The Markov chain is strictly sequential, but only ~0.3-15 % of proposals change the state.  The 32
 //     lanes therefore evaluate the next 32 proposals SPECULATIVELY against the current lattice and keep
 //     what they read — the 5x5 bit window around the source, which contains every cell adjacent to source
 //     or target — in a register.  The lowest accepted lane commits; every later lane patches its window
-//     with the two flipped cells (register arithmetic, exact) and re-derives its decision only if a bit
-//     really changed; then the next accepted lane commits.
-//     All 32 steps retire every batch and the retired sequence is exactly the sequential chain.
+//     with the two flipped cells (register arithmetic, exact) and re-derives its decision; then the next accepted
+//     lane commits.  All 32 steps retire every batch and the retired sequence is exactly the sequential chain.
+//   * Aggregation decides through a perfect hash of the 8 neighbourhood cells into a per-instance threshold table, and
+//     its commit rounds are straight-line code that commits up to two non-interacting candidates per round
+//     (resolve_batch_agg); the other behaviours re-derive only lanes whose window changed (resolve_batch).
 //   * Both RNG modes are counter based: fast = Philox2x32-10 keyed per step; verify = the WyRand
 //     double chain, whose draw count per step (2 or 3) depends on the state — resolved per batch by a
-//     warp-uniform walk over the "possible" ballots.
+//     warp scan over the lanes' alignment-automaton transition maps.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
