@@ -192,7 +192,12 @@ __host__ __device__ __forceinline__ uint32_t win25_patch(uint32_t x, uint32_t de
     const uint32_t w = v + delta;
     const bool vin = ((v | (v + 0x0303u)) & 0xFFFFF8F8u) == 0u;   // both fields in 0..4 (a borrow sets high bits)
     const bool win_ = ((w | (w + 0x0303u)) & 0xFFFFF8F8u) == 0u;
-    const uint32_t iv = (v & 7u) * (uint32_t)WS + (v >> 8), iw = (w & 7u) * (uint32_t)WS + (w >> 8);
+    // bit index WS*row + col of a valid cell: one byte-wise dot product of (row, col, 0, 0) with (WS, 1, 0, 0)
+#ifdef __CUDA_ARCH__
+    const uint32_t iv = __dp4a(v, (uint32_t)WS | 0x0100u, 0u), iw = __dp4a(w, (uint32_t)WS | 0x0100u, 0u);
+#else
+    const uint32_t iv = (v & 0xffu) * (uint32_t)WS + ((v >> 8) & 0xffu), iw = (w & 0xffu) * (uint32_t)WS + ((w >> 8) & 0xffu);
+#endif
     const uint32_t mv = 1u << (iv & 31u), mw = 1u << (iw & 31u);
     return (vin ? mv : 0u) ^ (win_ ? mw : 0u);
 }
@@ -381,13 +386,14 @@ __device__ __forceinline__ bool probe_possible(const Lat& L, uint32_t idx, uint3
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 // the committing lane's own lattice update, in two halves so the loads can be issued early
+// (w0 / w1 are written by lane f only; the other lanes' values are never stored anywhere)
 __device__ __forceinline__ void own_cells_load(uint32_t lane, uint32_t f, uint32_t a_ws, uint32_t a_wt, uint32_t& w0, uint32_t& w1) {
     asm volatile(
         "{\n\t.reg .pred q;\n\t"
         "setp.eq.u32 q, %2, %3;\n\t"
         "@q ld.shared.b32 %0, [%4];\n\t"
         "@q ld.shared.b32 %1, [%5];\n\t}"
-        : "+r"(w0), "+r"(w1) : "r"(lane), "r"(f), "r"(a_ws), "r"(a_wt) : "memory");
+        : "=r"(w0), "=r"(w1) : "r"(lane), "r"(f), "r"(a_ws), "r"(a_wt) : "memory");
 }
 __device__ __forceinline__ void own_cells_store(uint32_t lane, uint32_t f, uint32_t a_ws, uint32_t a_wt, uint32_t a_pos,
                                                 uint32_t v0, uint32_t v1, uint32_t t) {

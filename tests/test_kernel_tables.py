@@ -15,7 +15,8 @@ DIRS = [(-1, 0), (1, 0), (0, -1), (0, 1), (-1, -1), (1, 1)]          # mod.rs:80
 def tables(tmp_path_factory):
     from evosops_b200 import _build
     exe = str(tmp_path_factory.mktemp("tables") / "dump_tables")
-    subprocess.check_call([_build.nvcc_path(), "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "tools", "dump_tables.cu")])
+    subprocess.check_call([_build.nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O1", "-o", exe,
+                           os.path.join(ROOT, "tests", "tools", "dump_tables.cu")])
     return json.loads(subprocess.check_output([exe], text=True))
 
 
