@@ -197,9 +197,17 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"              # keep NCCL's version banner out of stdout: one JSON line only
+        # NCCL prints its version banner to stdout when it creates the communicator: point fd 1 at stderr until the
+        # first collective is through, so that stdout carries exactly ONE JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
 
     def barrier():
         torch.cuda.synchronize()
