@@ -291,10 +291,12 @@ __device__ __forceinline__ void derive(const Lat& L, const Geo& g, Prop& p) {
         // (integer arithmetic up to ONE final compare: chained predicates cost ~13 cycles each on the commit path,
         // and the load must not wait for the possible-ness test)
         const uint32_t thr = L.tab[p.mF + (((p.U0 & p.mB) * p.mM) >> 24)];
-        const uint32_t blocked = (uint32_t)p.bstat | ((p.U0 >> (p.tb & 31u)) & 1u);   // mod.rs:235-251
-        p.poss = blocked == 0u;
+        // p.tb is a one-hot MASK here: the target cell — or, when the target is statically not enterable, the source
+        // cell, which always holds this lane's own particle — so "possible" is one AND (mod.rs:235-251).  That
+        // predicate is ready long before the threshold arrives; the compare that feeds the vote just ANDs it in.
+        p.poss = (p.U0 & p.tb) == 0u;
         p.kind = p.poss ? 1u : 0u;
-        p.eff = p.pd < (thr & (blocked - 1u));               // mod.rs:284-285: possible and draw below the threshold
+        p.eff = p.poss && p.pd < thr;                        // mod.rs:284-285: possible and draw below the threshold
     } else if (BEH == LOCO) {
         uint32_t gi = (__popc(p.U0 & p.mB) * 3 + __popc(p.U0 & p.mM)) * 4 + __popc(p.U0 & p.mF);
         gi += p.aux & 0xffu;
@@ -343,7 +345,7 @@ template <int BEH, int RW>
 __device__ __forceinline__ void load_proposal(const Lat& L, const Geo& g, Prop& p) {
     p.s = L.pos[p.idx];
     const uint4 dt = L.dirtab[p.d];
-    p.mB = dt.x; p.mM = dt.y; p.mF = dt.z; p.tb = dt.w >> 16;
+    p.mB = dt.x; p.mM = dt.y; p.mF = dt.z; p.tb = dt.w >> 16;   // (AGG: turned into a mask once bstat is known, below)
     p.t = (p.s + dt.w) & 0xffffu;
     p.tt = p.t | (dt.w & 0xffff0000u);
     const uint32_t sr = p.s & 0xff, sc = p.s >> 8, tr = p.t & 0xff, tc = p.t >> 8;
@@ -356,6 +358,7 @@ __device__ __forceinline__ void load_proposal(const Lat& L, const Geo& g, Prop& 
         p.aux = sep_colour(g, p.idx);
     } else {
         p.bstat = Plane<RW>::bit(L.p1, tr, tc);
+        if (BEH == AGG) p.tb = 1u << (p.bstat ? (uint32_t)(2 * WS + 2) : (p.tb & 31u));
         if (BEH == COAT) p.U1 = win25<RW>(L.p2, sr, sc);
         if (BEH == LOCO) {                                   // locomotion.rs:230-235, 596-598
             const int a = (int)g.a, sx = (int)sr - 2, sy = (int)sc - 2, tx = (int)tr - 2, ty = (int)tc - 2;
