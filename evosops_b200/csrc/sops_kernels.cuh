@@ -267,7 +267,8 @@ struct Prop {
     uint32_t idx, d, pd;            // particle, direction, probability draw (0..999): fixed for the step
     uint32_t s, t;                  // packed padded source / target
     uint32_t tt;                    // t | tbit << 16 | SEP: flipped colour bits << 28 (what an accepted lane broadcasts)
-    uint32_t mB, mM, mF, tb;        // BACK / MID / FRONT masks in the 5x5 window, bit index of the target cell
+    uint32_t mB, mM, mF, tb;        // BACK / MID / FRONT masks in the 5x5 window; tb: SEP bit index of the target cell, else a
+                                    // one-hot mask (target cell, or the source cell when the target is statically blocked)
                                     // (AGG: mB = mask of all 8 cells, mM = hash multiplier, mF = table offset)
     uint32_t U0;                    // 5x5 window of plane p0 around s
     uint32_t U1;                    // SEP: 5x5 window of plane p1.  COAT: object window (static)
@@ -301,7 +302,7 @@ __device__ __forceinline__ void derive(const Lat& L, const Geo& g, Prop& p) {
         uint32_t gi = (__popc(p.U0 & p.mB) * 3 + __popc(p.U0 & p.mM)) * 4 + __popc(p.U0 & p.mF);
         gi += p.aux & 0xffu;
         const uint32_t thr = L.thr[gi];
-        p.poss = !p.bstat && !((p.U0 >> (p.tb & 31u)) & 1u);         // mod.rs:235-251
+        p.poss = (p.U0 & p.tb) == 0u;                        // locomotion.rs:551-568 (p.tb: the one-hot mask described above)
         p.kind = p.poss ? 1u : 0u;
         p.eff = p.poss && p.pd < thr;                        // mod.rs:284-285
     } else if (BEH == COAT) {
@@ -309,7 +310,7 @@ __device__ __forceinline__ void derive(const Lat& L, const Geo& g, Prop& p) {
         const uint32_t m = coat_idx2(__popc(p.U0 & p.mM), __popc(p.U1 & p.mM));
         const uint32_t f = coat_idx3(__popc(p.U0 & p.mF), __popc(p.U1 & p.mF));
         const uint32_t thr = L.thr[(b * 6 + m) * 10 + f];
-        p.poss = !p.bstat && !((p.U0 >> (p.tb & 31u)) & 1u);         // coating.rs:515-530 (object cells are in bstat)
+        p.poss = (p.U0 & p.tb) == 0u;                        // coating.rs:515-530 (object cells are in bstat, hence in the mask)
         p.kind = p.poss ? 1u : 0u;
         p.eff = p.poss && p.pd < thr;
     } else {
@@ -345,7 +346,7 @@ template <int BEH, int RW>
 __device__ __forceinline__ void load_proposal(const Lat& L, const Geo& g, Prop& p) {
     p.s = L.pos[p.idx];
     const uint4 dt = L.dirtab[p.d];
-    p.mB = dt.x; p.mM = dt.y; p.mF = dt.z; p.tb = dt.w >> 16;   // (AGG: turned into a mask once bstat is known, below)
+    p.mB = dt.x; p.mM = dt.y; p.mF = dt.z; p.tb = dt.w >> 16;   // (all but SEP: turned into a mask once bstat is known, below)
     p.t = (p.s + dt.w) & 0xffffu;
     p.tt = p.t | (dt.w & 0xffff0000u);
     const uint32_t sr = p.s & 0xff, sc = p.s >> 8, tr = p.t & 0xff, tc = p.t >> 8;
@@ -358,7 +359,7 @@ __device__ __forceinline__ void load_proposal(const Lat& L, const Geo& g, Prop& 
         p.aux = sep_colour(g, p.idx);
     } else {
         p.bstat = Plane<RW>::bit(L.p1, tr, tc);
-        if (BEH == AGG) p.tb = 1u << (p.bstat ? (uint32_t)(2 * WS + 2) : (p.tb & 31u));
+        p.tb = 1u << (p.bstat ? (uint32_t)(2 * WS + 2) : (p.tb & 31u));   // AGG / COAT / LOCO: see derive
         if (BEH == COAT) p.U1 = win25<RW>(L.p2, sr, sc);
         if (BEH == LOCO) {                                   // locomotion.rs:230-235, 596-598
             const int a = (int)g.a, sx = (int)sr - 2, sy = (int)sc - 2, tx = (int)tr - 2, ty = (int)tc - 2;
