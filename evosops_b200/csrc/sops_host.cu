@@ -103,7 +103,7 @@ struct Group {                      // one kernel launch: instances of one row-w
     size_t dump_off;                // word offset of this group's dump area
     int wpb, blocks;
     int cta_w;                      // 0: warp-per-instance kernel; else warps per instance of the CTA kernel
-    uint32_t variant;               // AGG commit-round form (KParams::variant)
+    int rounds;                     // commit-round form of the warp kernel (sops::ROUNDS_*)
     size_t smem;
 };
 
@@ -189,12 +189,12 @@ int fail(sops_ctx* c, int code, const std::string& msg) {
 
 typedef void (*kernel_fn)(const KParams);
 
-template <int BEH>
+template <int BEH, int ROUNDS>
 kernel_fn pick_kernel(int rw, int mode) {
-    if (rw == 1) return mode == 0 ? sops::sops_chain_kernel<BEH, 1, 0> : sops::sops_chain_kernel<BEH, 1, 1>;
-    if (rw == 2) return mode == 0 ? sops::sops_chain_kernel<BEH, 2, 0> : sops::sops_chain_kernel<BEH, 2, 1>;
-    if (rw == 4) return mode == 0 ? sops::sops_chain_kernel<BEH, 4, 0> : sops::sops_chain_kernel<BEH, 4, 1>;
-    return mode == 0 ? sops::sops_chain_kernel<BEH, 8, 0> : sops::sops_chain_kernel<BEH, 8, 1>;
+    if (rw == 1) return mode == 0 ? sops::sops_chain_kernel<BEH, 1, 0, ROUNDS> : sops::sops_chain_kernel<BEH, 1, 1, ROUNDS>;
+    if (rw == 2) return mode == 0 ? sops::sops_chain_kernel<BEH, 2, 0, ROUNDS> : sops::sops_chain_kernel<BEH, 2, 1, ROUNDS>;
+    if (rw == 4) return mode == 0 ? sops::sops_chain_kernel<BEH, 4, 0, ROUNDS> : sops::sops_chain_kernel<BEH, 4, 1, ROUNDS>;
+    return mode == 0 ? sops::sops_chain_kernel<BEH, 8, 0, ROUNDS> : sops::sops_chain_kernel<BEH, 8, 1, ROUNDS>;
 }
 // row width class of a padded grid side: 32-bit words per lattice row
 int rw_of(uint32_t pg) { return pg <= 32 ? 1 : pg <= 64 ? 2 : pg <= 128 ? 4 : 8; }
@@ -207,12 +207,15 @@ kernel_fn kernel_for_cta(int beh, int rw) {
     default: return rw == 1 ? sops::sops_chain_cta_kernel<sops::LOCO, 1, 4> : sops::sops_chain_cta_kernel<sops::LOCO, 2, 4>;
     }
 }
-kernel_fn kernel_for(int beh, int rw, int mode) {
+// rounds: sops::ROUNDS_PARALLEL (aggregation, coating) or sops::ROUNDS_SERIAL (every behaviour)
+bool has_parallel_rounds(int beh) { return beh == SOPS_AGG || beh == SOPS_COAT; }
+kernel_fn kernel_for(int beh, int rw, int mode, int rounds) {
+    const bool par = rounds == sops::ROUNDS_PARALLEL && has_parallel_rounds(beh);
     switch (beh) {
-    case SOPS_AGG: return pick_kernel<sops::AGG>(rw, mode);
-    case SOPS_SEP: return pick_kernel<sops::SEP>(rw, mode);
-    case SOPS_COAT: return pick_kernel<sops::COAT>(rw, mode);
-    default: return pick_kernel<sops::LOCO>(rw, mode);
+    case SOPS_AGG: return par ? pick_kernel<sops::AGG, sops::ROUNDS_PARALLEL>(rw, mode) : pick_kernel<sops::AGG, sops::ROUNDS_SERIAL>(rw, mode);
+    case SOPS_SEP: return pick_kernel<sops::SEP, sops::ROUNDS_SERIAL>(rw, mode);
+    case SOPS_COAT: return par ? pick_kernel<sops::COAT, sops::ROUNDS_PARALLEL>(rw, mode) : pick_kernel<sops::COAT, sops::ROUNDS_SERIAL>(rw, mode);
+    default: return pick_kernel<sops::LOCO, sops::ROUNDS_SERIAL>(rw, mode);
     }
 }
 
@@ -478,7 +481,13 @@ int sops_batch_prepare(sops_ctx* ctx, int behavior, const uint8_t* genomes, uint
             } else {
                 // launch geometry: spread few instances over all SMs, otherwise fill the machine with
                 // 8-warp CTAs that pull instances from a work counter
-                kernel_fn fn = kernel_for(behavior, grp.rw, rng_mode);
+                // commit rounds: all accepted lanes at once where the behaviour has that form (the caller may force
+                // either form; the bits are the same)
+                grp.rounds = has_parallel_rounds(behavior) ? sops::ROUNDS_PARALLEL : sops::ROUNDS_SERIAL;
+                if (behavior == SOPS_AGG && grp.count > 8u * (uint32_t)d.n_sm) grp.rounds = sops::ROUNDS_SERIAL;
+                if (flags & SOPS_F_ROUNDS_SERIAL) grp.rounds = sops::ROUNDS_SERIAL;
+                if ((flags & SOPS_F_ROUNDS_PARALLEL) && has_parallel_rounds(behavior)) grp.rounds = sops::ROUNDS_PARALLEL;
+                kernel_fn fn = kernel_for(behavior, grp.rw, rng_mode, grp.rounds);
                 int wpb = 8;
                 bool one_per_scheduler = false;
                 if (grp.count <= 8u * (uint32_t)d.n_sm) {
@@ -506,9 +515,6 @@ int sops_batch_prepare(sops_ctx* ctx, int behavior, const uint8_t* genomes, uint
                 uint32_t cap = (uint32_t)per_sm * (uint32_t)d.n_sm;
                 grp.blocks = (int)std::min(want, cap);
                 if (one_per_scheduler) grp.blocks = std::min(grp.blocks, d.n_sm);
-                // aggregation commit rounds: the straight-line two-per-round form is built for few, latency-bound
-                // chains; with the machine full, issue slots are the limit and the "touched lanes only" form wins
-                grp.variant = grp.count > 8u * (uint32_t)d.n_sm ? 1u : 0u;
             }
             d.groups.push_back(grp);
         }
@@ -566,9 +572,8 @@ int sops_batch_launch(sops_ctx* ctx) {
             kp.words_per_warp = g.words_per_warp;
             kp.off_p0 = g.off_p0; kp.off_p1 = g.off_p1; kp.off_p2 = g.off_p2;
             kp.off_pos = g.off_pos; kp.off_thr = g.off_thr; kp.off_aux = g.off_aux; kp.off_tab = g.off_tab;
-            { const char* v = getenv("SOPS_AGG_VARIANT"); kp.variant = v ? (uint32_t)atoi(v) : g.variant; }   // env: experiments only
             kp.plane_words = g.plane_words; kp.pos_words = g.pos_words;
-            kernel_fn fn = g.cta_w ? kernel_for_cta(ctx->behavior, g.rw) : kernel_for(ctx->behavior, g.rw, ctx->rng_mode);
+            kernel_fn fn = g.cta_w ? kernel_for_cta(ctx->behavior, g.rw) : kernel_for(ctx->behavior, g.rw, ctx->rng_mode, g.rounds);
             cudaStream_t st = d.stream;
             if (gi > 0) st = d.stream2;                      // independent chains: the two classes run concurrently
             fn<<<g.blocks, g.wpb * 32, g.smem, st>>>(kp);

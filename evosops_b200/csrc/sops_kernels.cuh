@@ -31,6 +31,9 @@ namespace sops {
 
 enum { AGG = 0, SEP = 1, COAT = 2, LOCO = 3 };
 enum { MODE_VERIFY = 0, MODE_FAST = 1 };
+// commit-round form of the warp kernel: all accepted lanes at once (fixed-point patch rounds; aggregation, coating) or
+// one commit per round with re-derivation of the lanes whose window changed (every behaviour)
+enum { ROUNDS_PARALLEL = 0, ROUNDS_SERIAL = 1 };
 
 struct Instance {                   // 40 bytes, built on the host, sorted by cost (longest first)
     uint64_t seed;                  // init seed (StdRng::seed_from_u64)
@@ -62,7 +65,6 @@ struct KParams {
     uint32_t words_per_warp;
     uint32_t off_p0, off_p1, off_p2, off_pos, off_thr, off_aux;
     uint32_t off_tab;               // AGG: hashed-window threshold table, SOPS_AGG_TAB_WORDS words
-    uint32_t variant;               // AGG: 0 = straight-line commit rounds, 1 = "touched lanes only" rounds
     uint32_t plane_words, pos_words;
 };
 
@@ -210,6 +212,24 @@ __host__ __device__ __forceinline__ bool near_sources(uint32_t a, uint32_t b) {
     return ((dd | (dd + 0x0101u)) & 0xFFFFF8F8u) == 0u;
 }
 
+// Patch look-up table for the parallel commit rounds (resolve_batch_jacobi): what a committed move s_f -> s_f + D[d]
+// flips in the 5x5 window centred at ANOTHER lane's source s_l, by [d][s_f.row - s_l.row + 3][s_f.col - s_l.col + 3]
+// (offsets -3..3: the target can lie inside the window when the source is one cell outside).  Bit 31: s_f == s_l (the
+// same particle was proposed again: that lane is stale once f commits); bit 30: the move's target is s_l (SEP: lane l
+// proposed the swap partner).  Window bits are 0..28, so the flags never reach a decision mask.
+__host__ __device__ constexpr uint32_t plut_entry(int d, int r3, int c3) {
+    const int r = r3 - 3, c = c3 - 3, tr = r + dir_dr(d), tc = c + dir_dc(d);
+    uint32_t m = 0;
+    if (r >= -2 && r <= 2 && c >= -2 && c <= 2) m ^= 1u << (WS * (r + 2) + (c + 2));
+    if (tr >= -2 && tr <= 2 && tc >= -2 && tc <= 2) m ^= 1u << (WS * (tr + 2) + (tc + 2));
+    if (r == 0 && c == 0) m |= 0x80000000u;
+    if (tr == 0 && tc == 0) m |= 0x40000000u;
+    return m;
+}
+#define SOPS_PLUT_WORDS (6u * 49u)
+// byte offset of entry [d][r3][c3] as ONE dp4a of the packed (r3 | c3 << 8 | d << 16) with these byte weights
+#define SOPS_PLUT_DP4A 0x00C4041Cu                          // 4 * (7, 1, 49, 0)
+
 // group index tables --------------------------------------------------------------------------------
 // separation.rs:205-222: (occupied c, same colour k) -> c(c+1)/2 + (c-k)
 __device__ __forceinline__ uint32_t sep_idx(uint32_t c, uint32_t k) { return ((c * (c + 1)) >> 1) + (c - k); }
@@ -230,7 +250,8 @@ struct Lat {
     uint32_t* p0; uint32_t* p1; uint32_t* p2;
     uint16_t* pos; uint16_t* thr; uint16_t* light;
     uint16_t* tab;                  // AGG: thresholds by [direction][window hash]
-    uint32_t variant;
+    uint32_t plut;                  // shared-window address of the patch look-up table (per CTA)
+    uint4* cmp;                     // this warp's scratch list of accepted moves (32 entries)
     const uint4* dirtab;            // per direction: back5, mid5, front5 masks, delta | tbit << 16
                                     // (AGG: all-8-cells mask, hash multiplier, table offset, delta | tbit << 16)
 };
@@ -526,154 +547,116 @@ __device__ __forceinline__ void commit_and_repair(const Lat& L, const Geo& g, ui
     }
 }
 
-// --- aggregation: straight-line commit rounds ---------------------------------------------------------------
-// Same protocol as resolve_batch below, arranged so one commit round is branch-free and short.  A chain that accepts
-// often is bound by the instructions ONE warp can issue per round (integer ops: one per two cycles), so the round
-// is written for instruction count:
-//   * every lane re-derives after every commit (AGG's decision is one multiply + one load, cheaper than a divergent
-//     "touched lanes only" region); lanes at or before the committing lane keep the window they retired with, and a
-//     lane that committed (or is inactive) carries pd = 0xffffffff, which no threshold exceeds;
-//   * a lane that proposed the particle that just moved is STALE: it joins the candidate set and is re-evaluated from
-//     the lattice when it becomes the lowest candidate (everything before it is committed by then) — a warp-uniform,
-//     rare branch instead of a divergent region in every round;
-//   * the committing lane updates the lattice itself: predicated loads and stores (no atomics: ptxas wraps a predicated
-//     shared atomic in a divergent region) on word addresses and masks every lane prepared once per batch from its
-//     OWN proposal — nothing is recomputed from the broadcast move, the loads are issued before the broadcast returns;
-//   * the lowest candidate of the next round is selected (one find-leading-one on the isolated lowest bit) and its
-//     move broadcast before the loop branch, so the vote -> branch latency hides behind them.
-template <int BEH, int RW, bool VERIFY>
-__device__ __forceinline__ uint32_t resolve_batch_agg(const Lat& L, const Geo& g, uint32_t lane, bool active, Prop& p, uint32_t& ncommit) {
-    constexpr bool PAIR = !VERIFY;                           // commit two candidates per round when they cannot interact
-    uint32_t R = 32;
-    uint32_t stale = 0;                                      // warp-uniform lane mask
-    // VERIFY: a lane below the cut R still has the possible-ness it was aligned with (a flip cuts the batch there)
-    const bool poss0 = p.poss;
-    if (!__any_sync(0xffffffffu, p.eff)) return R;           // most batches of a low-acceptance chain end here
-    uint32_t A = __ballot_sync(0xffffffffu, p.eff);
-    uint32_t low = A & (0u - A);                             // lowest candidate as a one-hot mask (0: none)
-    const uint32_t lane_g = active ? lane : 0u;              // an inactive lane is never "later than f": never patched, never stale
-    // this lane's own commit, prepared once: word addresses and bit masks of its two cells, its position slot
-    uint32_t a_ws, a_wt, m_s, m_t, org;
-    const uint32_t a_pos = smem_addr(L.pos + p.idx);
-    auto prepare = [&]() {
-        a_ws = smem_addr(Plane<RW>::word(L.p0, p.s & 0xff, p.s >> 8));
-        a_wt = smem_addr(Plane<RW>::word(L.p0, p.t & 0xff, p.t >> 8));
-        m_s = 1u << ((p.s >> 8) & 31u);
-        m_t = 1u << ((p.t >> 8) & 31u);
-        if (a_ws == a_wt) m_s = m_t = m_s ^ m_t;             // both cells in one word: the two stores write the same value
-        org = p.s - 0x0202u;
-    };
-    auto revote = [&]() {
-        __syncwarp();
-        derive<BEH>(L, g, p);
-        if (VERIFY) {
-            const uint32_t X = __ballot_sync(0xffffffffu, active && p.poss != poss0) & lowmask(R) & ~stale;
-            if (X) R = (uint32_t)__ffs(X) - 1;
-        }
-        A = __ballot_sync(0xffffffffu, p.eff) | stale;
-        if (VERIFY) A &= lowmask(R);
-        low = A & (0u - A);
-    };
-    // the candidates of the upcoming round: the lowest, and (PAIR) the second-lowest unless it is stale; their moves
-    uint32_t low2 = 0, f1, f2r = 0xffffffffu, sf1, tf1, sf2 = 0, tf2 = 0;
-    auto select = [&]() {
-        f1 = bfind32(low);                                   // 0xffffffff for "none": the shuffles then read lane 31, unused
-        sf1 = __shfl_sync(0xffffffffu, p.s, f1);
-        tf1 = __shfl_sync(0xffffffffu, p.t, f1);
-        if (PAIR) {
-            const uint32_t rest = A & (A - 1u);               // A without its lowest bit (when low is 0, A is too)
-            low2 = rest & (0u - rest) & ~stale;
-            f2r = bfind32(low2);
-            sf2 = __shfl_sync(0xffffffffu, p.s, f2r);
-            tf2 = __shfl_sync(0xffffffffu, p.t, f2r);
-        }
-    };
-    prepare();
-    select();
-    for (;;) {
-        uint32_t dU2 = 0;
-        bool viol = false;
-        // ---- fast rounds: one straight-line body, one branch at the bottom ----
-        while (low & ~stale) {
-            // c1 flips cells within distance 1 of sf1; c2 decides from cells within distance 2 of sf2: with the two
-            // sources more than 3 apart (Chebyshev) neither move can change the other's decision or particle
-            uint32_t l2 = 0, f2 = 0xffffffffu;
-            if (PAIR) {
-                l2 = near_sources(sf1, sf2) ? 0u : low2;
-                f2 = l2 ? f2r : 0xffffffffu;
-            }
-            // lanes strictly between the two saw c1 only; if one of them is a candidate afterwards it precedes c2
-            const uint32_t between = l2 ? ((l2 - 1u) & ~(low | (low - 1u))) : 0u;
-            const bool later1 = lane_g > f1, later2 = PAIR && lane_g > f2;
-            uint32_t w0 = 0, w1 = 0;
-            own_cells_load(lane, f1, a_ws, a_wt, w0, w1);
-            uint32_t dU1 = win25_patch(sf1, tf1 - sf1, org);
-            asm volatile("" : "+r"(dU1));                    // keep the patch arithmetic out of a divergent branch
-            dU1 = later1 ? dU1 : 0u;
-            if (PAIR) {
-                dU2 = win25_patch(sf2, tf2 - sf2, org);
-                asm volatile("" : "+r"(dU2));
-                dU2 = later2 ? dU2 : 0u;
-            }
-            const uint32_t st1 = __ballot_sync(0xffffffffu, later1 && p.s == sf1);   // proposed the moved particle again
-            const uint32_t st2 = PAIR ? __ballot_sync(0xffffffffu, later2 && p.s == sf2) : 0u;
-            p.U0 ^= dU1 ^ dU2;
-            own_cells_store(lane, f1, a_ws, a_wt, a_pos, w0 ^ m_s, w1 ^ m_t, p.t);
-            p.pd = lane == f1 ? 0xffffffffu : p.pd;
-            uint32_t x0 = 0, x1 = 0;
-            if (PAIR) own_cells_load(lane, f2, a_ws, a_wt, x0, x1);   // after c1's stores: the two moves may share a word
-            stale |= st1;
-            __syncwarp();
-            derive<BEH>(L, g, p);
-            if (VERIFY) {
-                const uint32_t X = __ballot_sync(0xffffffffu, active && p.poss != poss0) & lowmask(R) & ~stale;
-                if (X) R = (uint32_t)__ffs(X) - 1;
-            }
-            const uint32_t E = __ballot_sync(0xffffffffu, p.eff);
-            viol = PAIR && ((E | stale) & between) != 0u;    // rare: c2 has to wait (handled below the loop)
-            const uint32_t f2c = viol ? 0xffffffffu : f2;
-            if (PAIR) {
-                own_cells_store(lane, f2c, a_ws, a_wt, a_pos, x0 ^ m_s, x1 ^ m_t, p.t);
-                p.pd = lane == f2c ? 0xffffffffu : p.pd;
-            }
-#ifdef SOPS_COUNT_ROUNDS                                     // diagnostic build: "committed" counts commit rounds instead
-            ncommit += 1u;
-#else
-            ncommit += 1u + ((PAIR && l2 != 0u && !viol) ? 1u : 0u);
+// --- parallel commit rounds (aggregation, coating) --------------------------------------------------------------
+// The sequential chain asks, for lane l:  decision_l = g(window_l(S0) ^ XOR of the moves of the ACCEPTED lanes f < l).
+// That is a fixed point of a strictly lower-triangular map over the 32 lanes, solved by iteration instead of one
+// commit after the other:
+//   1. every lane XORs into P the exact patch of every currently accepted earlier lane (a warp-uniform loop over the
+//      accepted set; one shuffle + one table load per accepted lane, all independent of each other);
+//   2. every lane re-derives from W0 ^ P; the accepted set is voted again; lanes whose decision changed are toggled
+//      in (their patch is XORed in or out of the later lanes) and step 2 repeats — rarely: a patched window seldom
+//      flips a decision;
+//   3. all accepted lanes commit AT ONCE: shared-memory atomics on the lattice words, one position store each.
+// A lane that proposed the particle an earlier accepted lane moves holds the wrong window altogether (stale): the batch
+// is cut at the lowest such lane (returned bound R, as for VERIFY's alignment cuts; the caller restarts there).
+// Exactness: at the fixed point every lane below R decided on exactly the window the sequential chain shows it.
+// m = s_f | d_f << 16 | f << 24 (what lane f publishes), bias = 0x0303 - s_l, mykey = l << 24: the patch of f's move
+// in lane l's window if f < l, else 0.  (Sentinel m = 0xffffffff: never earlier than anybody.)
+__device__ __forceinline__ uint32_t plut_fetch(uint32_t m, uint32_t bias, uint32_t lut, uint32_t mykey) {
+    const uint32_t v = m + bias;                             // (s_f - s_l + 3) per byte | d << 16 | f << 24 (garbage above a byte that borrows)
+    const uint32_t z = (v | (v + 0x0101u)) & 0xF8F8u;        // both offsets in 0..6?
+    uint32_t dU = 0;
+#ifdef __CUDA_ARCH__
+    const uint32_t addr = __dp4a(v, SOPS_PLUT_DP4A, lut);
+    asm("{\n\t.reg .pred q, r;\n\t"
+        "setp.lt.u32 r, %2, %3;\n\t"
+        "setp.eq.and.u32 q, %1, 0, r;\n\t"
+        "@q ld.shared.b32 %0, [%4];\n\t}"
+        : "+r"(dU) : "r"(z), "r"(m), "r"(mykey), "r"(addr));
 #endif
-            stale |= viol ? 0u : st2;
-            A = (E & ~l2) | stale;
-            if (VERIFY) A &= lowmask(R);
-            low = viol ? 0u : (A & (0u - A));
-            select();
-        }
-        if (!low && !viol) break;                            // the common exit: one test
-        if (viol) {                                          // undo c2's patch; it is selected again after the re-vote
-            p.U0 ^= dU2;
-            revote();
-            select();
-            continue;
-        }
-        // the lowest candidate is stale: it re-reads the lattice (everything before it is committed) and is an ordinary
-        // candidate from then on — warp-uniform, rare
-        if (lane == f1) { load_proposal<BEH, RW>(L, g, p); prepare(); }
-        stale ^= low;
-        revote();
-        select();
+    return dU;
+}
+// XOR the patches of the lanes in X (warp-uniform mask) into P, for the lanes after each of them; two per trip
+// (the rare re-vote path: the first pass reads the compacted list instead)
+__device__ __forceinline__ void toggle_patches(uint32_t X, uint32_t desc, uint32_t bias, uint32_t lut, uint32_t mykey, uint32_t& P) {
+    while (X) {
+        const uint32_t f1 = (uint32_t)__ffs(X) - 1u;
+        X &= X - 1u;
+        const uint32_t f2 = X ? (uint32_t)__ffs(X) - 1u : 0xffffffffu;
+        X &= X - 1u;
+        const uint32_t m1 = __shfl_sync(0xffffffffu, desc, f1);
+        uint32_t m2 = __shfl_sync(0xffffffffu, desc, f2);
+        m2 = f2 == 0xffffffffu ? 0xffffffffu : m2;
+        P ^= plut_fetch(m1, bias, lut, mykey) ^ plut_fetch(m2, bias, lut, mykey);
     }
-    return R;
+}
+template <int BEH, int RW, bool VERIFY>
+__device__ __forceinline__ uint32_t resolve_batch_jacobi(const Lat& L, const Geo& g, uint32_t lane, bool active, Prop& p, uint32_t& ncommit) {
+    uint32_t Acur = __ballot_sync(0xffffffffu, p.eff);       // the lanes whose moves the later lanes' P holds
+    if (!Acur) return 32;                                    // most batches of a low-acceptance chain end here
+    const bool poss0 = p.poss;                               // VERIFY: the possible-ness this lane's draws were aligned with
+    const uint32_t W0 = p.U0;
+    const uint32_t mykey = lane << 24;
+    const uint32_t desc = p.s | (p.d << 16) | mykey;
+    const uint32_t bias = 0x0303u - p.s;
+    // the accepted lanes' moves, compacted in lane order into the warp's scratch list (every lane writes one entry:
+    // the others fill the rest with sentinels), then read back four at a time by broadcast loads
+    const uint32_t below = lowmask(lane);
+    const uint32_t K = (uint32_t)__popc(Acur);
+    {
+        const uint32_t slot = p.eff ? (uint32_t)__popc(Acur & below) : K + (uint32_t)__popc(~Acur & below);
+        reinterpret_cast<uint32_t*>(L.cmp)[slot] = p.eff ? desc : 0xffffffffu;
+    }
+    __syncwarp();
+    auto block = [&](uint32_t b) -> uint32_t {
+        const uint4 m = L.cmp[b];
+        return plut_fetch(m.x, bias, L.plut, mykey) ^ plut_fetch(m.y, bias, L.plut, mykey) ^
+               plut_fetch(m.z, bias, L.plut, mykey) ^ plut_fetch(m.w, bias, L.plut, mykey);
+    };
+    uint32_t P = block(0);
+    if (K > 4) {
+        P ^= block(1);
+#pragma unroll 1
+        for (uint32_t b = 2; 4 * b < K; ++b) P ^= block(b);
+    }
+    bool acc = p.eff;
+    uint32_t S;
+    for (;;) {
+        // stale lanes proposed a particle that an earlier accepted lane moves: the batch is cut at the lowest one (the
+        // flag's parity is exact there: its first earlier mover is the only one below it that is not stale itself)
+        S = __ballot_sync(0xffffffffu, active && (P >> 31) != 0u);
+        p.U0 = W0 ^ P;
+        derive<BEH>(L, g, p);
+        if (!__any_sync(0xffffffffu, p.eff != acc)) break;   // fixed point: every lane decided on the window it is shown
+        const uint32_t X = __ballot_sync(0xffffffffu, p.eff != acc);
+        toggle_patches(X, desc, bias, L.plut, mykey, P);
+        Acur ^= X;
+        acc = p.eff;
+    }
+    if (VERIFY) S |= __ballot_sync(0xffffffffu, active && p.poss != poss0);   // a flipped possible-ness shifts every later draw: cut there too
+    const uint32_t keep = ~S & (S - 1u);                     // the lanes below the lowest cut lane (all of them when S == 0)
+    const uint32_t C = Acur & keep;
+    const bool mine = (C >> lane) & 1u;
+    {
+        // every lane issues the two atomics (a zero mask for the lanes that do not commit): no divergent region
+        uint32_t* ws = const_cast<uint32_t*>(Plane<RW>::word(L.p0, p.s & 0xff, p.s >> 8));
+        uint32_t* wt = const_cast<uint32_t*>(Plane<RW>::word(L.p0, p.t & 0xff, p.t >> 8));
+        atomicXor(ws, mine ? 1u << ((p.s >> 8) & 31u) : 0u);
+        atomicXor(wt, mine ? 1u << ((p.t >> 8) & 31u) : 0u);
+        if (mine) L.pos[p.idx] = (uint16_t)p.t;
+    }
+    __syncwarp();
+    ncommit += (uint32_t)__popc(C);
+    return (uint32_t)__popc(keep);
 }
 
 // --- commit rounds of one speculative batch ---------------------------------------------------------------
 // On entry every active lane holds a proposal evaluated against the current lattice; lane order = chain
 // order.  VERIFY: a repair that flips a lane's possible-ness changes how many draws that step consumes, so
 // the batch is cut at that lane (returned bound R; lanes >= R are not retired).  ncommit is warp-uniform.
-template <int BEH, int RW, bool VERIFY>
+template <int BEH, int RW, bool VERIFY, int ROUNDS>
 __device__ __forceinline__ uint32_t resolve_batch(const Lat& L, const Geo& g, uint32_t lane, bool active, Prop& p, uint32_t& ncommit) {
-    // (COAT commits the same way and runs bit-exact through resolve_batch_agg<COAT> too, but its decision — six POPCs and
-    // three table steps — is too dear to repeat in every lane after every commit: measured +5 % at p_acc 0.5, -20 % at
-    // p_acc 0.02, so only aggregation is dispatched there.)
-    if (BEH == AGG && L.variant == 0) return resolve_batch_agg<BEH, RW, VERIFY>(L, g, lane, active, p, ncommit);
+    if (ROUNDS == ROUNDS_PARALLEL) return resolve_batch_jacobi<BEH, RW, VERIFY>(L, g, lane, active, p, ncommit);
     uint32_t R = 32;
     for (;;) {
         uint32_t A = __ballot_sync(0xffffffffu, p.eff);
@@ -870,7 +853,7 @@ __device__ __forceinline__ void fitness(const KParams& P, const Lat& L, const Ge
 }
 
 // --- one instance, start to finish ------------------------------------------------------------------
-template <int BEH, int RW, int MODE>
+template <int BEH, int RW, int MODE, int ROUNDS>
 __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, const Instance& in, uint32_t lane) {
     Geo g;
     g.a = in.arena; g.G = 2 * g.a + 1; g.orient = in.orient;
@@ -890,33 +873,46 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
         // Every batch retires 32 consecutive steps; the random numbers of batch b+1 do not depend on the
         // lattice, so they are drawn while batch b's shared-memory loads are in flight.
         const uint32_t key = (uint32_t)ms, khi = (uint32_t)(ms >> 32);
-        const uint64_t nfull = steps >> 5;
-        const uint32_t tail = (uint32_t)steps & 31u;
-        auto draw = [&](uint64_t st, Prop& q) {
+        // one step's draws packed in a word: particle | direction << 16 | probability draw << 19
+        auto draw = [&](uint64_t st) -> uint32_t {
             uint32_t r0, r1;
             philox2x32_10((uint32_t)st, (uint32_t)(st >> 32) ^ khi, key, r0, r1);
-            q.idx = __umulhi(r0, n);
             const uint64_t m6 = (uint64_t)r1 * 6u;
-            q.d = (uint32_t)(m6 >> 32);
-            q.pd = __umulhi((uint32_t)m6, 1000u);
+            return __umulhi(r0, n) | ((uint32_t)(m6 >> 32) << 16) | (__umulhi((uint32_t)m6, 1000u) << 19);
+        };
+        auto unpack = [&](uint32_t w, Prop& q) { q.idx = w & 0xffffu; q.d = (w >> 16) & 7u; q.pd = w >> 19; };
+        // A batch normally retires its 32 steps; the parallel commit rounds may cut it at a lane R < 32 (a lane that
+        // proposed a particle an earlier lane of the batch moved): the next batch then starts at that step, and the
+        // draws move down by R lanes (this batch's upper lanes, the prefetched batch's lower ones).
+        auto realign = [&](uint32_t curw, uint32_t nxtw, uint32_t R) -> uint32_t {
+            const uint32_t src = lane + R;
+            const uint32_t lo = __shfl_sync(0xffffffffu, curw, src), hi = __shfl_sync(0xffffffffu, nxtw, src);
+            return src < 32 ? lo : hi;
         };
         Prop cur;
-        draw((uint64_t)lane, cur);
-        for (uint64_t b = 0; b < nfull; ++b) {
-            Prop nxt;
-            draw(((b + 1) << 5) + lane, nxt);
+        uint32_t curw = draw((uint64_t)lane);
+        uint64_t k = 0;                                      // steps retired
+        while (k + 32 <= steps) {
+            const uint32_t nxtw = draw(k + 32 + lane);
+            unpack(curw, cur);
             evaluate<BEH, RW>(L, g, cur);
-            resolve_batch<BEH, RW, false>(L, g, lane, true, cur, ncommit);
-            nposs += cur.poss;
-            cur.idx = nxt.idx; cur.d = nxt.d; cur.pd = nxt.pd;
+            const uint32_t R = resolve_batch<BEH, RW, false, ROUNDS>(L, g, lane, true, cur, ncommit);
+            nposs += (cur.poss && lane < R) ? 1u : 0u;
+            curw = R == 32 ? nxtw : realign(curw, nxtw, R);
+            k += R;
         }
-        if (tail) {
+        while (k < steps) {
+            const uint32_t tail = (uint32_t)(steps - k);     // 1..31
             const bool active = lane < tail;
-            if (!active) cur.pd = 0xffffffffu;               // never accepted, also when AGG re-derives after a commit
+            unpack(curw, cur);
+            if (!active) cur.pd = 0xffffffffu;               // never accepted, also when a commit round re-derives
             evaluate<BEH, RW>(L, g, cur);
             if (!active) { cur.eff = false; cur.poss = false; }
-            resolve_batch<BEH, RW, false>(L, g, lane, active, cur, ncommit);
-            nposs += (active && cur.poss) ? 1u : 0u;
+            uint32_t R = resolve_batch<BEH, RW, false, ROUNDS>(L, g, lane, active, cur, ncommit);
+            if (R > tail) R = tail;
+            nposs += (active && cur.poss && lane < R) ? 1u : 0u;
+            curw = realign(curw, curw, R);                   // (lanes past the end of the chain get recycled draws: inactive)
+            k += R;
         }
     } else {
         // Verification mode: the number of draws a step consumes (2 if blocked, 3 if possible) decides
@@ -972,7 +968,7 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
             evaluate<BEH, RW>(L, g, p);
             if (!active) { p.eff = false; p.poss = false; }
             const uint32_t am = __ballot_sync(0xffffffffu, active);
-            const uint32_t R = resolve_batch<BEH, RW, true>(L, g, lane, active, p, ncommit);
+            const uint32_t R = resolve_batch<BEH, RW, true, ROUNDS>(L, g, lane, active, p, ncommit);
             nposs += (active && p.poss && lane < R) ? 1u : 0u;
             k += __popc(am & lowmask(R));
             if (R < 32) cbase += 2 * R + __shfl_sync(0xffffffffu, (uint32_t)myO, R);   // the cut lane restarts the next batch
@@ -1019,15 +1015,19 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
 #ifndef SOPS_MIN_BLOCKS
 #define SOPS_MIN_BLOCKS 1
 #endif
-template <int BEH, int RW, int MODE>
+template <int BEH, int RW, int MODE, int ROUNDS>
 __global__ void __launch_bounds__(256, BEH == AGG ? 3 : SOPS_MIN_BLOCKS) sops_chain_kernel(const KParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint4 s_dirtab[8];
+    __shared__ uint32_t s_plut[SOPS_PLUT_WORDS];
+    __shared__ uint4 s_cmp[8][8];                            // per warp: the compacted accepted moves of a batch
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int d = 0; d < 6; ++d)
             s_dirtab[d] = dirtab_entry<BEH>(d);
     }
+    for (uint32_t k = threadIdx.x; k < SOPS_PLUT_WORDS; k += blockDim.x)
+        s_plut[k] = plut_entry((int)(k / 49u), (int)((k % 49u) / 7u), (int)(k % 7u));
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* base = smem + (size_t)warp * P.words_per_warp;
@@ -1037,15 +1037,16 @@ __global__ void __launch_bounds__(256, BEH == AGG ? 3 : SOPS_MIN_BLOCKS) sops_ch
     L.thr = reinterpret_cast<uint16_t*>(base + P.off_thr);
     L.light = reinterpret_cast<uint16_t*>(base + P.off_aux);
     L.tab = reinterpret_cast<uint16_t*>(base + P.off_tab);
-    L.variant = P.variant;
     L.dirtab = s_dirtab;
+    L.plut = smem_addr(s_plut);
+    L.cmp = s_cmp[warp];
     for (;;) {
         uint32_t q = 0;
         if (lane == 0) q = atomicAdd(P.work_counter, 1u);
         q = __shfl_sync(0xffffffffu, q, 0);
         if (q >= P.n_inst) break;
         const Instance in = P.inst[q];
-        run_instance<BEH, RW, MODE>(P, L, in, lane);
+        run_instance<BEH, RW, MODE, ROUNDS>(P, L, in, lane);
     }
 }
 
@@ -1175,8 +1176,9 @@ __global__ void __launch_bounds__(32 * W) sops_chain_cta_kernel(const KParams P)
     L.thr = reinterpret_cast<uint16_t*>(smem + P.off_thr);
     L.light = reinterpret_cast<uint16_t*>(smem + P.off_aux);
     L.tab = reinterpret_cast<uint16_t*>(smem + P.off_tab);
-    L.variant = P.variant;
     L.dirtab = s_dirtab;
+    L.plut = 0;                                              // (the parallel commit rounds are a warp-kernel form)
+    L.cmp = nullptr;
     for (;;) {
         __syncthreads();                                     // previous instance fully retired (s_q, lattice reusable)
         if (tid == 0) s_q = atomicAdd(P.work_counter, 1u);

@@ -66,7 +66,11 @@ enum {
     SOPS_F_THEORY_TABLE = 4,/* use theory_gene_probability() (mod.rs:91-93, separation.rs:82-84)   */
     /* Kernel choice (results are bit-identical either way; default: one warp per chain) */
     SOPS_F_FORCE_WARP = 8,  /* one warp per chain (the default, spelled out)                        */
-    SOPS_F_FORCE_CTA = 16   /* one 4-warp CTA per chain (fast mode): pays for few, low-acceptance chains */
+    SOPS_F_FORCE_CTA = 16,  /* one 4-warp CTA per chain (fast mode): pays for few, low-acceptance chains */
+    /* Commit-round form of the warp kernel (bit-identical; default: chosen from the batch size) */
+    SOPS_F_ROUNDS_SERIAL = 32,   /* one commit per round, only lanes whose window changed re-derive          */
+    SOPS_F_ROUNDS_PARALLEL = 64  /* all accepted lanes of a batch commit at once (fixed-point patch rounds;
+                                    aggregation and coating; ignored by the other behaviours)               */
 };
 
 /* Create a context over n_dev CUDA devices (device_ids NULL -> devices 0..n_dev-1). */

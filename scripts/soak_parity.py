@@ -1,7 +1,6 @@
 """Soak run of the GPU-vs-oracle parity check (final lattice, particle list, integers, counters) over many random cases,
-biased towards high-acceptance genomes, both aggregation commit-round forms.  Not part of the test-suite: a one-off
+biased towards high-acceptance genomes, every commit-round form.  Not part of the test-suite: a one-off
 confidence run (usage: python scripts/soak_parity.py [cases] [seed])."""
-import os
 import sys
 import numpy as np
 sys.path.insert(0, ".")
@@ -32,8 +31,8 @@ for case in range(n_cases):
     orient = rng.integers(1, 4, size=(2, 2)).astype(np.uint8) if beh == E.LOCO else None
     steps = int(rng.integers(1, 60000))
     rng_mode = int(rng.integers(0, 2))
-    os.environ["SOPS_AGG_VARIANT"] = str(int(rng.integers(0, 2)))
     kflag = E.F_FORCE_CTA if (rng_mode == E.RNG_FAST and a <= 29 and rng.integers(0, 4) == 0) else 0
+    kflag |= int(rng.choice([0, E.F_ROUNDS_SERIAL, E.F_ROUNDS_PARALLEL]))
     got, want, cnt = run_pair(ctx, beh, gs, [size, size], seeds, rng_mode, steps=steps, move_seeds=ms, orient=orient, flags=kflag)
     check_equal(ctx, beh, gs, [size, size], seeds, got, want, cnt, rng_mode, steps, move_seeds=ms, orient=orient, flags=kflag)
     done += 1

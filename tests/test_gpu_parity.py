@@ -121,21 +121,36 @@ def test_agg_many_seeds_short_chains(ctx, genomes, rng_mode, kflag):
     check_equal(ctx, E.AGG, gs, sizes, seeds, got, want, cnt, rng_mode, 300000, move_seeds=ms, dump_every=3, flags=kflag)
 
 
-@pytest.mark.parametrize("variant", ["0", "1"], ids=["straight-line", "touched-only"])
+ROUNDS = {"parallel": E.F_ROUNDS_PARALLEL, "serial": E.F_ROUNDS_SERIAL}
+
+
+@pytest.mark.parametrize("rounds", ["parallel", "serial"])
 @pytest.mark.parametrize("rng_mode", [E.RNG_VERIFY, E.RNG_FAST])
-def test_agg_commit_rounds_under_heavy_acceptance(ctx, genomes, rng_mode, variant, monkeypatch):
+def test_agg_commit_rounds_under_heavy_acceptance(ctx, genomes, rng_mode, rounds):
     # genomes that accept (almost) every possible move: many candidates per 32-step batch, so the commit rounds run
-    # their rare paths all the time — two commits per round, a candidate turning up between the pair (undo), lanes
-    # that proposed the particle that just moved (stale, re-read).  Both commit-round forms, RW 1 and 2.
-    monkeypatch.setenv("SOPS_AGG_VARIANT", variant)          # read by the library at launch time (experiments knob)
+    # their rare paths all the time — many commits per batch, decisions flipped by an earlier commit, lanes that
+    # proposed the particle that just moved (stale: the parallel rounds cut the batch there).  Every commit-round
+    # form (SOPS_F_ROUNDS_*), RW 1 and 2.
     rng = np.random.default_rng(7)
     gs = np.stack([np.zeros(48, dtype=np.uint8), np.ones(48, dtype=np.uint8),
                    rng.integers(0, 3, size=48, dtype=np.uint8), genomes["agg_random"]])
     sizes = [(6, 3), (6, 1), (10, 7), (13, 9), (20, 14), (9, 2)]
     seeds = [3, 4, 5, 6, 7, 8]
-    got, want, cnt = run_pair(ctx, E.AGG, gs, sizes, seeds, rng_mode, steps=120001)
-    check_equal(ctx, E.AGG, gs, sizes, seeds, got, want, cnt, rng_mode, 120001)
+    got, want, cnt = run_pair(ctx, E.AGG, gs, sizes, seeds, rng_mode, steps=120001, flags=ROUNDS[rounds])
+    check_equal(ctx, E.AGG, gs, sizes, seeds, got, want, cnt, rng_mode, 120001, flags=ROUNDS[rounds])
     assert cnt[2] > 0.1 * cnt[0]                              # the batch really is acceptance-heavy
+
+
+@pytest.mark.parametrize("rounds", ["parallel", "serial"])
+@pytest.mark.parametrize("rng_mode", [E.RNG_VERIFY, E.RNG_FAST])
+def test_coat_commit_rounds_under_heavy_acceptance(ctx, rng_mode, rounds):
+    rng = np.random.default_rng(8)
+    gs = np.stack([np.zeros(600, dtype=np.uint8), rng.integers(0, 2, size=600, dtype=np.uint8)])
+    sizes = [(12, 2, 1), (20, 5, 2), (26, 8, 4), (30, 6, 3)]
+    seeds = [3, 4, 5, 6]
+    got, want, cnt = run_pair(ctx, E.COAT, gs, sizes, seeds, rng_mode, steps=100001, flags=ROUNDS[rounds])
+    check_equal(ctx, E.COAT, gs, sizes, seeds, got, want, cnt, rng_mode, 100001, flags=ROUNDS[rounds])
+    assert cnt[2] > 0.1 * cnt[0]
 
 
 def test_agg_large_batch_takes_the_throughput_form(ctx, genomes):
