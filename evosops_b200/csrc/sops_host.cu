@@ -98,7 +98,7 @@ struct Group {                      // one kernel launch: instances of one row-w
     int rw;
     uint32_t first, count;          // range in the device's instance array
     uint32_t plane_words, pos_words, words_per_warp;
-    uint32_t off_p0, off_p1, off_p2, off_pos, off_thr, off_aux, off_tab;
+    uint32_t off_p0, off_p1, off_p2, off_pos, off_thr, off_aux, off_tab, inv_words;
     uint32_t dump_stride;
     size_t dump_off;                // word offset of this group's dump area
     int wpb, blocks;
@@ -208,12 +208,18 @@ kernel_fn kernel_for_cta(int beh, int rw) {
     }
 }
 // rounds: sops::ROUNDS_PARALLEL (aggregation, coating) or sops::ROUNDS_SERIAL (every behaviour)
-bool has_parallel_rounds(int beh) { return beh == SOPS_AGG || beh == SOPS_COAT; }
+// (separation keeps a cell -> particle map for it: one- and two-word rows only, 2 or 6 KB per chain)
+bool has_parallel_rounds(int beh, int rw) { return beh == SOPS_AGG || beh == SOPS_COAT || (beh == SOPS_SEP && rw <= 2); }
+template <int ROUNDS>
+kernel_fn pick_sep_narrow(int rw, int mode) {
+    if (rw == 1) return mode == 0 ? sops::sops_chain_kernel<sops::SEP, 1, 0, ROUNDS> : sops::sops_chain_kernel<sops::SEP, 1, 1, ROUNDS>;
+    return mode == 0 ? sops::sops_chain_kernel<sops::SEP, 2, 0, ROUNDS> : sops::sops_chain_kernel<sops::SEP, 2, 1, ROUNDS>;
+}
 kernel_fn kernel_for(int beh, int rw, int mode, int rounds) {
-    const bool par = rounds == sops::ROUNDS_PARALLEL && has_parallel_rounds(beh);
+    const bool par = rounds == sops::ROUNDS_PARALLEL && has_parallel_rounds(beh, rw);
     switch (beh) {
     case SOPS_AGG: return par ? pick_kernel<sops::AGG, sops::ROUNDS_PARALLEL>(rw, mode) : pick_kernel<sops::AGG, sops::ROUNDS_SERIAL>(rw, mode);
-    case SOPS_SEP: return pick_kernel<sops::SEP, sops::ROUNDS_SERIAL>(rw, mode);
+    case SOPS_SEP: return par ? pick_sep_narrow<sops::ROUNDS_PARALLEL>(rw, mode) : pick_kernel<sops::SEP, sops::ROUNDS_SERIAL>(rw, mode);
     case SOPS_COAT: return par ? pick_kernel<sops::COAT, sops::ROUNDS_PARALLEL>(rw, mode) : pick_kernel<sops::COAT, sops::ROUNDS_SERIAL>(rw, mode);
     default: return pick_kernel<sops::LOCO, sops::ROUNDS_SERIAL>(rw, mode);
     }
@@ -233,6 +239,11 @@ void layout_group(Group& g, int beh, uint32_t max_pg, uint32_t max_n) {
     g.off_thr = off; off += thr_words;
     g.off_aux = off; if (beh == SOPS_LOCO) off += SOPS_LOCO_AUX_WORDS;
     g.off_tab = off; if (beh == SOPS_AGG) off += SOPS_AGG_TAB_WORDS;
+    g.inv_words = 0;
+    if (beh == SOPS_SEP && g.rounds == sops::ROUNDS_PARALLEL) {   // cell -> particle map, u16 per cell, 32 * rw cells per row
+        g.inv_words = (max_pg * 32u * (uint32_t)g.rw + 1u) / 2u;
+        off += g.inv_words;
+    }
     off = (off + 1u) & ~1u;
     off |= 2u;                                                  // stride = 2 mod 4 words: spreads warps over banks, keeps 8-byte alignment
     g.words_per_warp = off;
@@ -461,13 +472,20 @@ int sops_batch_prepare(sops_ctx* ctx, int behavior, const uint8_t* genomes, uint
                 ctx->where[q] = std::make_pair((int)di, in.slot);
                 d.global_of.push_back(q);
             }
+            // kernel choice: one warp per chain, unless the caller asks for the 4-warp CTA-per-chain variant
+            // (fast mode only; it pays when few chains with very low acceptance run, i.e. late GA generations)
+            grp.cta_w = (rng_mode == SOPS_RNG_FAST && (flags & SOPS_F_FORCE_CTA) && !(flags & SOPS_F_FORCE_WARP) && grp.rw <= 2) ? 4 : 0;
+            // commit rounds of the warp kernel: all accepted lanes at once where the behaviour has that form (the caller
+            // may force either form; the bits are the same)
+            grp.rounds = has_parallel_rounds(behavior, grp.rw) ? sops::ROUNDS_PARALLEL : sops::ROUNDS_SERIAL;
+            if (behavior == SOPS_AGG && grp.count > 8u * (uint32_t)d.n_sm) grp.rounds = sops::ROUNDS_SERIAL;
+            if (flags & SOPS_F_ROUNDS_SERIAL) grp.rounds = sops::ROUNDS_SERIAL;
+            if ((flags & SOPS_F_ROUNDS_PARALLEL) && has_parallel_rounds(behavior, grp.rw)) grp.rounds = sops::ROUNDS_PARALLEL;
+            if (grp.cta_w) grp.rounds = sops::ROUNDS_SERIAL;
             layout_group(grp, behavior, max_pg, max_n);
             grp.dump_off = dump_words;
             if (flags & SOPS_F_DUMP) dump_words += (size_t)grp.count * grp.dump_stride;
-            // kernel choice: one warp per chain, unless the caller asks for the 4-warp CTA-per-chain variant
-            // (fast mode only; it pays when few chains with very low acceptance run, i.e. late GA generations)
             const size_t smem_per_warp = (size_t)grp.words_per_warp * 4;
-            grp.cta_w = (rng_mode == SOPS_RNG_FAST && (flags & SOPS_F_FORCE_CTA) && !(flags & SOPS_F_FORCE_WARP) && grp.rw <= 2) ? 4 : 0;
             int per_sm = 0;
             if (grp.cta_w) {
                 kernel_fn fn = kernel_for_cta(behavior, grp.rw);
@@ -481,12 +499,6 @@ int sops_batch_prepare(sops_ctx* ctx, int behavior, const uint8_t* genomes, uint
             } else {
                 // launch geometry: spread few instances over all SMs, otherwise fill the machine with
                 // 8-warp CTAs that pull instances from a work counter
-                // commit rounds: all accepted lanes at once where the behaviour has that form (the caller may force
-                // either form; the bits are the same)
-                grp.rounds = has_parallel_rounds(behavior) ? sops::ROUNDS_PARALLEL : sops::ROUNDS_SERIAL;
-                if (behavior == SOPS_AGG && grp.count > 8u * (uint32_t)d.n_sm) grp.rounds = sops::ROUNDS_SERIAL;
-                if (flags & SOPS_F_ROUNDS_SERIAL) grp.rounds = sops::ROUNDS_SERIAL;
-                if ((flags & SOPS_F_ROUNDS_PARALLEL) && has_parallel_rounds(behavior)) grp.rounds = sops::ROUNDS_PARALLEL;
                 kernel_fn fn = kernel_for(behavior, grp.rw, rng_mode, grp.rounds);
                 int wpb = 8;
                 bool one_per_scheduler = false;
@@ -573,6 +585,7 @@ int sops_batch_launch(sops_ctx* ctx) {
             kp.off_p0 = g.off_p0; kp.off_p1 = g.off_p1; kp.off_p2 = g.off_p2;
             kp.off_pos = g.off_pos; kp.off_thr = g.off_thr; kp.off_aux = g.off_aux; kp.off_tab = g.off_tab;
             kp.plane_words = g.plane_words; kp.pos_words = g.pos_words;
+            kp.inv_words = g.inv_words;
             kernel_fn fn = g.cta_w ? kernel_for_cta(ctx->behavior, g.rw) : kernel_for(ctx->behavior, g.rw, ctx->rng_mode, g.rounds);
             cudaStream_t st = d.stream;
             if (gi > 0) st = d.stream2;                      // independent chains: the two classes run concurrently

@@ -64,7 +64,8 @@ struct KParams {
     // (PG = G + 4) so the 5x5 window of any particle stays inside the plane.
     uint32_t words_per_warp;
     uint32_t off_p0, off_p1, off_p2, off_pos, off_thr, off_aux;
-    uint32_t off_tab;               // AGG: hashed-window threshold table, SOPS_AGG_TAB_WORDS words
+    uint32_t off_tab;               // AGG: hashed-window threshold table, SOPS_AGG_TAB_WORDS words.  SEP (parallel rounds): inverse map
+    uint32_t inv_words;             // SEP: words of the cell -> particle map (0: not kept)
     uint32_t plane_words, pos_words;
 };
 
@@ -174,6 +175,10 @@ template <> struct Plane<2> {       // padded grid side <= 64: one u64 per row
     static __device__ __forceinline__ void atom_xor(uint32_t* p, uint32_t r, uint32_t c) { atomicXor(&p[2 * r + (c >> 5)], 1u << (c & 31)); }
     static __device__ __forceinline__ const uint32_t* word(const uint32_t* p, uint32_t r, uint32_t c) { return p + 2 * r + (c >> 5); }
 };
+
+// SEP, parallel rounds: index of a packed cell in the cell -> particle map (u16 entries, 32 * RW per row)
+template <int RW>
+__device__ __forceinline__ uint32_t inv_index(uint32_t cell) { return (cell & 0xffu) * (32u * RW) + (cell >> 8); }
 
 // 3x3 window around padded cell (r, c): bit = 3*row + col (fitness sums)
 template <int RW>
@@ -592,8 +597,9 @@ __device__ __forceinline__ void toggle_patches(uint32_t X, uint32_t desc, uint32
 }
 template <int BEH, int RW, bool VERIFY>
 __device__ __forceinline__ uint32_t resolve_batch_jacobi(const Lat& L, const Geo& g, uint32_t lane, bool active, Prop& p, uint32_t& ncommit) {
+    const bool any = __any_sync(0xffffffffu, p.eff);         // (both votes are issued before the branch: it waits for the first only)
     uint32_t Acur = __ballot_sync(0xffffffffu, p.eff);       // the lanes whose moves the later lanes' P holds
-    if (!Acur) return 32;                                    // most batches of a low-acceptance chain end here
+    if (!any) return 32;                                     // most batches of a low-acceptance chain end here
     const bool poss0 = p.poss;                               // VERIFY: the possible-ness this lane's draws were aligned with
     const uint32_t W0 = p.U0;
     const uint32_t mykey = lane << 24;
@@ -613,9 +619,8 @@ __device__ __forceinline__ uint32_t resolve_batch_jacobi(const Lat& L, const Geo
         return plut_fetch(m.x, bias, L.plut, mykey) ^ plut_fetch(m.y, bias, L.plut, mykey) ^
                plut_fetch(m.z, bias, L.plut, mykey) ^ plut_fetch(m.w, bias, L.plut, mykey);
     };
-    uint32_t P = block(0);
-    if (K > 4) {
-        P ^= block(1);
+    uint32_t P = block(0) ^ block(1);                        // eight entries up front (sentinels past the K-th), the rest rarely
+    if (K > 8) {
 #pragma unroll 1
         for (uint32_t b = 2; 4 * b < K; ++b) P ^= block(b);
     }
@@ -650,12 +655,94 @@ __device__ __forceinline__ uint32_t resolve_batch_jacobi(const Lat& L, const Geo
     return (uint32_t)__popc(keep);
 }
 
+// --- parallel commit rounds, separation ----------------------------------------------------------------------------
+// Same fixed point as above with three differences.  (1) What a lane's move flips depends on its own decision: a move
+// carries the mover's colour, a swap exchanges two colours (x = colour bits flipped at both cells) — so a lane's
+// published descriptor can change from one iteration to the next even while it stays accepted, and every iteration
+// rebuilds the compacted list and the patches from scratch (iterations past the first are rare).  (2) A swap moves a
+// SECOND particle: a lane that proposed the swap partner is stale too (table bit 30, counted for swaps only), and a
+// swapping lane whose target cell an earlier accepted lane changes cannot know its partner's identity from the S0
+// inverse map — both cut the batch like the mover-stale lanes do.  Flags are OR-accumulated here (two swaps can hit the
+// same lane).  (3) The partner's index comes from an inverse map cell -> particle kept beside the colour planes
+// (the reference scans `participants` for it, separation.rs:302).
+template <int RW, bool VERIFY>
+__device__ __forceinline__ uint32_t resolve_batch_jacobi_sep(const Lat& L, const Geo& g, uint32_t lane, bool active, Prop& p, uint32_t& ncommit) {
+    if (!__any_sync(0xffffffffu, p.eff)) return 32;
+    const uint32_t W00 = p.U0, W01 = p.U1;
+    const uint32_t mykey = lane << 27;
+    const uint32_t base_desc = p.s | (p.d << 16) | mykey;
+    const uint32_t bias = 0x0303u - p.s;
+    const uint32_t below = lowmask(lane);
+    const uint32_t tmask = 1u << (p.tb & 31u);               // the target cell in this lane's window
+    uint32_t A, S;
+    for (;;) {
+        A = __ballot_sync(0xffffffffu, p.eff);
+        const uint32_t K = (uint32_t)__popc(A);
+        {   // descriptor of the current decision: flipped colour bits at 24..25, "swap" at 26
+            const uint32_t desc = base_desc | (((p.tt >> 28) & 3u) << 24) | ((p.tt >> 31) << 26);
+            const uint32_t slot = p.eff ? (uint32_t)__popc(A & below) : K + (uint32_t)__popc(~A & below);
+            reinterpret_cast<uint32_t*>(L.cmp)[slot] = p.eff ? desc : 0xffffffffu;
+        }
+        __syncwarp();
+        uint32_t P0 = 0, P1 = 0;
+        S = 0;
+#pragma unroll 1
+        for (uint32_t b = 0; 4 * b < K; ++b) {
+            const uint4 m4 = L.cmp[b];
+            const uint32_t mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t m = mm[i];
+                uint32_t dU = plut_fetch(m, bias, L.plut, mykey);
+                dU &= (m & (1u << 26)) ? 0xffffffffu : 0xbfffffffu;      // the partner flag counts for swaps only
+                P0 ^= (m & (1u << 24)) ? dU : 0u;
+                P1 ^= (m & (1u << 25)) ? dU : 0u;
+                S |= dU;
+            }
+        }
+        p.U0 = W00 ^ (P0 & 0x1fffffffu);
+        p.U1 = W01 ^ (P1 & 0x1fffffffu);
+        const bool eff0 = p.eff;
+        const uint32_t tt0 = p.tt;
+        derive<SEP>(L, g, p);
+        const bool changed = (p.eff != eff0) || (p.eff && ((p.tt ^ tt0) >> 28) != 0u);
+        __syncwarp();                                        // the list is rewritten by the next iteration
+        if (!__any_sync(0xffffffffu, changed)) break;
+    }
+    const bool cut = (S >> 30) != 0u || ((S & tmask) != 0u && p.kind == 2u);
+    const uint32_t Sb = __ballot_sync(0xffffffffu, active && cut);
+    const uint32_t keep = ~Sb & (Sb - 1u);
+    const uint32_t C = A & keep;
+    if ((C >> lane) & 1u) {
+        const uint32_t x = (p.tt >> 28) & 3u;
+        const bool swap = (p.tt >> 31) != 0u;
+        uint32_t* ws = const_cast<uint32_t*>(Plane<RW>::word(L.p0, p.s & 0xff, p.s >> 8));
+        uint32_t* wt = const_cast<uint32_t*>(Plane<RW>::word(L.p0, p.t & 0xff, p.t >> 8));
+        const uint32_t plane1 = (uint32_t)(L.p1 - L.p0);
+        const uint32_t ms_ = 1u << ((p.s >> 8) & 31u), mt_ = 1u << ((p.t >> 8) & 31u);
+        if (x & 1u) { atomicXor(ws, ms_); atomicXor(wt, mt_); }
+        if (x & 2u) { atomicXor(ws + plane1, ms_); atomicXor(wt + plane1, mt_); }
+        const uint32_t is = inv_index<RW>(p.s), it = inv_index<RW>(p.t);
+        if (swap) {
+            const uint32_t partner = L.tab[it];
+            L.pos[partner] = (uint16_t)p.s;
+            L.tab[is] = (uint16_t)partner;
+        }
+        L.pos[p.idx] = (uint16_t)p.t;
+        L.tab[it] = (uint16_t)p.idx;
+    }
+    __syncwarp();
+    ncommit += (uint32_t)__popc(C);
+    return (uint32_t)__popc(keep);
+}
+
 // --- commit rounds of one speculative batch ---------------------------------------------------------------
 // On entry every active lane holds a proposal evaluated against the current lattice; lane order = chain
 // order.  VERIFY: a repair that flips a lane's possible-ness changes how many draws that step consumes, so
 // the batch is cut at that lane (returned bound R; lanes >= R are not retired).  ncommit is warp-uniform.
 template <int BEH, int RW, bool VERIFY, int ROUNDS>
 __device__ __forceinline__ uint32_t resolve_batch(const Lat& L, const Geo& g, uint32_t lane, bool active, Prop& p, uint32_t& ncommit) {
+    if (ROUNDS == ROUNDS_PARALLEL && BEH == SEP) return resolve_batch_jacobi_sep<RW, VERIFY>(L, g, lane, active, p, ncommit);
     if (ROUNDS == ROUNDS_PARALLEL) return resolve_batch_jacobi<BEH, RW, VERIFY>(L, g, lane, active, p, ncommit);
     uint32_t R = 32;
     for (;;) {
@@ -754,6 +841,7 @@ __device__ __forceinline__ uint32_t init_instance(const KParams& P, const Lat& L
             if (acc && ord < g.n) {
                 L.pos[ord] = (uint16_t)cell;
                 if (BEH == SEP) {
+                    if (P.inv_words) L.tab[inv_index<RW>(cell)] = (uint16_t)ord;   // parallel rounds: cell -> particle
                     uint32_t col = sep_colour(g, ord);
                     if (col & 1) Plane<RW>::atom_or(L.p0, pr, pc);
                     if (col & 2) Plane<RW>::atom_or(L.p1, pr, pc);

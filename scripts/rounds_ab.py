@@ -68,3 +68,18 @@ if "coat" in which:
     for form, fl in (("parallel", E.F_ROUNDS_PARALLEL), ("serial", E.F_ROUNDS_SERIAL)):
         ms, c = timed(E.COAT, gc, csz, csd, fl, w=(0.65, 0.35))
         report("coat pop50 generation", form, ms, c)
+if "sep" in which:
+    rng = np.random.default_rng(3)
+    gsep = rng.integers(0, 11, size=(50, 600), dtype=np.uint8)
+    ssz, ssd = bench.trial_list([(13, 9)], [1, 2, 3, 4, 5])
+    for form, fl in (("parallel", E.F_ROUNDS_PARALLEL), ("serial", E.F_ROUNDS_SERIAL)):
+        ms, c = timed(E.SEP, gsep, ssz, ssd, fl, w=(0.65, 0.35))
+        report("sep pop50 x (13,9) x5 generation", form, ms, c)
+if "loco" in which:
+    rng = np.random.default_rng(4)
+    glo = rng.integers(0, 11, size=(50, 144), dtype=np.uint8)
+    lsz, lsd = bench.trial_list([(13, 9)], [1, 2, 3, 4, 5])
+    ori = (np.arange(250) % 3 + 1).astype(np.uint8)
+    for form, fl in (("parallel", E.F_ROUNDS_PARALLEL), ("serial", E.F_ROUNDS_SERIAL)):
+        ms, c = timed(E.LOCO, glo, lsz, lsd, fl, w=(0.75, 0.25), orient=ori)
+        report("loco pop50 x (13,9) x5 generation", form, ms, c)

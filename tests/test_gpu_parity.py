@@ -153,6 +153,20 @@ def test_coat_commit_rounds_under_heavy_acceptance(ctx, rng_mode, rounds):
     assert cnt[2] > 0.1 * cnt[0]
 
 
+@pytest.mark.parametrize("rounds", ["parallel", "serial"])
+@pytest.mark.parametrize("rng_mode", [E.RNG_VERIFY, E.RNG_FAST])
+def test_sep_commit_rounds_under_heavy_acceptance(ctx, genomes, rng_mode, rounds):
+    # separation with always-accept genomes: nearly every step is a move or a colour swap, so a 32-step batch holds
+    # many commits, swaps whose partner was proposed by a later lane, swaps into cells an earlier lane just changed
+    rng = np.random.default_rng(9)
+    gs = np.stack([np.zeros(600, dtype=np.uint8), rng.integers(0, 2, size=600, dtype=np.uint8), genomes["sep_random"]])
+    sizes = [(6, 3), (6, 1), (10, 7), (13, 9), (20, 14), (9, 2)]
+    seeds = [3, 4, 5, 6, 7, 8]
+    got, want, cnt = run_pair(ctx, E.SEP, gs, sizes, seeds, rng_mode, steps=100001, flags=ROUNDS[rounds])
+    check_equal(ctx, E.SEP, gs, sizes, seeds, got, want, cnt, rng_mode, 100001, flags=ROUNDS[rounds])
+    assert cnt[2] > 0.1 * cnt[0]
+
+
 def test_agg_large_batch_takes_the_throughput_form(ctx, genomes):
     # more chains than 8 per SM: the host picks the "touched lanes only" rounds and 8-warp CTAs; same bits
     gs = np.stack([np.zeros(48, dtype=np.uint8), genomes["agg_evolved"]])
