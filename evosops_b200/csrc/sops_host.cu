@@ -209,7 +209,7 @@ kernel_fn kernel_for_cta(int beh, int rw) {
 }
 // rounds: sops::ROUNDS_PARALLEL (aggregation, coating) or sops::ROUNDS_SERIAL (every behaviour)
 // (separation keeps a cell -> particle map for it: one- and two-word rows only, 2 or 6 KB per chain)
-bool has_parallel_rounds(int beh, int rw) { return beh == SOPS_AGG || beh == SOPS_COAT || (beh == SOPS_SEP && rw <= 2); }
+bool has_parallel_rounds(int beh, int rw) { return beh != SOPS_SEP || rw <= 2; }
 template <int ROUNDS>
 kernel_fn pick_sep_narrow(int rw, int mode) {
     if (rw == 1) return mode == 0 ? sops::sops_chain_kernel<sops::SEP, 1, 0, ROUNDS> : sops::sops_chain_kernel<sops::SEP, 1, 1, ROUNDS>;
@@ -221,7 +221,7 @@ kernel_fn kernel_for(int beh, int rw, int mode, int rounds) {
     case SOPS_AGG: return par ? pick_kernel<sops::AGG, sops::ROUNDS_PARALLEL>(rw, mode) : pick_kernel<sops::AGG, sops::ROUNDS_SERIAL>(rw, mode);
     case SOPS_SEP: return par ? pick_sep_narrow<sops::ROUNDS_PARALLEL>(rw, mode) : pick_kernel<sops::SEP, sops::ROUNDS_SERIAL>(rw, mode);
     case SOPS_COAT: return par ? pick_kernel<sops::COAT, sops::ROUNDS_PARALLEL>(rw, mode) : pick_kernel<sops::COAT, sops::ROUNDS_SERIAL>(rw, mode);
-    default: return pick_kernel<sops::LOCO, sops::ROUNDS_SERIAL>(rw, mode);
+    default: return par ? pick_kernel<sops::LOCO, sops::ROUNDS_PARALLEL>(rw, mode) : pick_kernel<sops::LOCO, sops::ROUNDS_SERIAL>(rw, mode);
     }
 }
 

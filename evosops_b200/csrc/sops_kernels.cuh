@@ -279,6 +279,14 @@ __device__ __forceinline__ uint32_t loco_sense(const uint16_t* light, uint32_t o
     return o == 1 ? (y >= (int)(f >> 8)) : (x >= (int)(f & 0xff));
 }
 
+// sensing against given beam fronts (light[b] = x | y << 8), packed like Prop::aux
+__device__ __forceinline__ uint32_t loco_aux(uint32_t o, int bs, int bt, uint32_t fs, uint32_t ft, int sx, int sy, int tx, int ty) {
+    const uint32_t cur = bs < 0 ? 0u : (o == 1 ? (uint32_t)(sy >= (int)(fs >> 8)) : (uint32_t)(sx >= (int)(fs & 0xff)));
+    const uint32_t fut = bt < 0 ? 0u : (o == 1 ? (uint32_t)(ty >= (int)(ft >> 8)) : (uint32_t)(tx >= (int)(ft & 0xff)));
+    const uint32_t li = (cur == fut) ? 2u : cur;             // (0,1)->0 (1,0)->1 else 2   (locomotion.rs:230-235)
+    return li * 48u | ((uint32_t)(bs + 1) << 8) | ((uint32_t)(bt + 1) << 16) | (cur << 24) | (fut << 25);
+}
+
 __device__ __forceinline__ uint32_t sep_colour(const Geo& g, uint32_t idx) {   // hand-out order, separation.rs:126-146
     return 1u + (idx >= g.n3) + (idx >= 2 * g.n3);
 }
@@ -300,6 +308,7 @@ struct Prop {
     uint32_t U1;                    // SEP: 5x5 window of plane p1.  COAT: object window (static)
     uint32_t aux;                   // LOCO: light_idx*48 | beam(s)+1 << 8 | beam(t)+1 << 16 | senses(s) << 24 | senses(t) << 25.  SEP: mover colour
     uint32_t kind;                  // 0 blocked, 1 move into empty, 2 swap (SEP)
+    uint32_t lfront;                // LOCO: the beam fronts this proposal sensed, light[beam(s)] | light[beam(t)] << 16
     bool bstat;                     // target statically not enterable
     bool poss, eff;                 // target enterable now; would change the state
 };
@@ -390,10 +399,9 @@ __device__ __forceinline__ void load_proposal(const Lat& L, const Geo& g, Prop& 
         if (BEH == LOCO) {                                   // locomotion.rs:230-235, 596-598
             const int a = (int)g.a, sx = (int)sr - 2, sy = (int)sc - 2, tx = (int)tr - 2, ty = (int)tc - 2;
             const int bs = loco_beam(g.orient, a, sx, sy), bt = loco_beam(g.orient, a, tx, ty);
-            const uint32_t cur = loco_sense(L.light, g.orient, bs, sx, sy);
-            const uint32_t fut = loco_sense(L.light, g.orient, bt, tx, ty);
-            const uint32_t li = (cur == fut) ? 2u : cur;     // (0,1)->0 (1,0)->1 else 2
-            p.aux = li * 48u | ((uint32_t)(bs + 1) << 8) | ((uint32_t)(bt + 1) << 16) | (cur << 24) | (fut << 25);
+            const uint32_t fs = L.light[bs < 0 ? 0 : bs], ft = L.light[bt < 0 ? 0 : bt];   // (unused when on no beam)
+            p.lfront = fs | (ft << 16);
+            p.aux = loco_aux(g.orient, bs, bt, fs, ft, sx, sy, tx, ty);
         }
     }
 }
@@ -595,6 +603,15 @@ __device__ __forceinline__ void toggle_patches(uint32_t X, uint32_t desc, uint32
         P ^= plut_fetch(m1, bias, lut, mykey) ^ plut_fetch(m2, bias, lut, mykey);
     }
 }
+// Locomotion adds the light table to this: an accepted move rewrites the front of the beam through its source (if the
+// mover senses light there) and of the beam through its target (if it will sense light there) (locomotion.rs:344-519, net
+// effect), and a later lane on one of those beams senses against the NEW front.  Writers are rare (a particle senses
+// light only at the front of its beam), so every iteration walks the currently accepted writers in lane order with
+// shuffles, gives each later lane the front of the latest earlier writer of its two beams, senses again and decides; a
+// lane whose written beams changed counts as changed.  The commit stores the fronts in lane order.
+__device__ __forceinline__ uint32_t loco_writes(uint32_t aux) {   // beams (+1) a move with this sensing rewrites: s-beam | t-beam << 8
+    return (((aux >> 24) & 1u) ? ((aux >> 8) & 0xffu) : 0u) | ((((aux >> 25) & 1u) ? ((aux >> 16) & 0xffu) : 0u) << 8);
+}
 template <int BEH, int RW, bool VERIFY>
 __device__ __forceinline__ uint32_t resolve_batch_jacobi(const Lat& L, const Geo& g, uint32_t lane, bool active, Prop& p, uint32_t& ncommit) {
     const bool any = __any_sync(0xffffffffu, p.eff);         // (both votes are issued before the branch: it waits for the first only)
@@ -624,19 +641,47 @@ __device__ __forceinline__ uint32_t resolve_batch_jacobi(const Lat& L, const Geo
 #pragma unroll 1
         for (uint32_t b = 2; 4 * b < K; ++b) P ^= block(b);
     }
+    // LOCO: this lane's beams (+1, 0 = none), cells in the light table's coordinates
+    const uint32_t bs1 = (p.aux >> 8) & 0xffu, bt1 = (p.aux >> 16) & 0xffu;
+    const int sx = (int)(p.s & 0xff) - 2, sy = (int)(p.s >> 8) - 2, tx = (int)(p.t & 0xff) - 2, ty = (int)(p.t >> 8) - 2;
+    const uint32_t su = (uint32_t)sx | ((uint32_t)sy << 8), tu = (uint32_t)tx | ((uint32_t)ty << 8);
     bool acc = p.eff;
+    uint32_t wr = 0;                                         // LOCO: the beams this lane's move is currently taken to rewrite
+    if (BEH == LOCO) wr = acc ? loco_writes(p.aux) : 0u;
     uint32_t S;
     for (;;) {
         // stale lanes proposed a particle that an earlier accepted lane moves: the batch is cut at the lowest one (the
         // flag's parity is exact there: its first earlier mover is the only one below it that is not stale itself)
         S = __ballot_sync(0xffffffffu, active && (P >> 31) != 0u);
         p.U0 = W0 ^ P;
+        if (BEH == LOCO) {
+            uint32_t Wb = __ballot_sync(0xffffffffu, wr != 0u);
+            uint32_t fs = p.lfront & 0xffffu, ft = p.lfront >> 16;
+            const uint32_t wa = wr | (su << 16);
+            while (Wb) {                                     // rare: some accepted move rewrites a beam front
+                const uint32_t f = (uint32_t)__ffs(Wb) - 1u;
+                Wb &= Wb - 1u;
+                const uint32_t w = __shfl_sync(0xffffffffu, wa, f), v2 = __shfl_sync(0xffffffffu, tu, f);
+                const uint32_t b1 = w & 0xffu, b2 = (w >> 8) & 0xffu, v1 = w >> 16;
+                const bool later = lane > f;
+                if (later && b1 != 0u) { fs = b1 == bs1 ? v1 : fs; ft = b1 == bt1 ? v1 : ft; }
+                if (later && b2 != 0u) { fs = b2 == bs1 ? v2 : fs; ft = b2 == bt1 ? v2 : ft; }
+            }
+            p.aux = loco_aux(g.orient, (int)bs1 - 1, (int)bt1 - 1, fs, ft, sx, sy, tx, ty);
+        }
         derive<BEH>(L, g, p);
-        if (!__any_sync(0xffffffffu, p.eff != acc)) break;   // fixed point: every lane decided on the window it is shown
+        bool changed = p.eff != acc;
+        uint32_t wr_new = 0;
+        if (BEH == LOCO) {
+            wr_new = p.eff ? loco_writes(p.aux) : 0u;
+            changed = changed || wr_new != wr;
+        }
+        if (!__any_sync(0xffffffffu, changed)) break;        // fixed point: every lane decided on the window it is shown
         const uint32_t X = __ballot_sync(0xffffffffu, p.eff != acc);
         toggle_patches(X, desc, bias, L.plut, mykey, P);
         Acur ^= X;
         acc = p.eff;
+        wr = wr_new;
     }
     if (VERIFY) S |= __ballot_sync(0xffffffffu, active && p.poss != poss0);   // a flipped possible-ness shifts every later draw: cut there too
     const uint32_t keep = ~S & (S - 1u);                     // the lanes below the lowest cut lane (all of them when S == 0)
@@ -649,6 +694,18 @@ __device__ __forceinline__ uint32_t resolve_batch_jacobi(const Lat& L, const Geo
         atomicXor(ws, mine ? 1u << ((p.s >> 8) & 31u) : 0u);
         atomicXor(wt, mine ? 1u << ((p.t >> 8) & 31u) : 0u);
         if (mine) L.pos[p.idx] = (uint16_t)p.t;
+    }
+    if (BEH == LOCO) {                                       // beam fronts, in lane order: the last writer of a beam wins
+        uint32_t Wm = __ballot_sync(0xffffffffu, mine && wr != 0u);
+        while (Wm) {
+            const uint32_t f = (uint32_t)__ffs(Wm) - 1u;
+            Wm &= Wm - 1u;
+            if (lane == f) {
+                if (wr & 0xffu) L.light[(wr & 0xffu) - 1u] = (uint16_t)su;
+                if (wr >> 8) L.light[(wr >> 8) - 1u] = (uint16_t)tu;
+            }
+            __syncwarp();
+        }
     }
     __syncwarp();
     ncommit += (uint32_t)__popc(C);

@@ -167,6 +167,21 @@ def test_sep_commit_rounds_under_heavy_acceptance(ctx, genomes, rng_mode, rounds
     assert cnt[2] > 0.1 * cnt[0]
 
 
+@pytest.mark.parametrize("rounds", ["parallel", "serial"])
+@pytest.mark.parametrize("rng_mode", [E.RNG_VERIFY, E.RNG_FAST])
+def test_loco_commit_rounds_under_heavy_acceptance(ctx, genomes, rng_mode, rounds):
+    # locomotion with always-accept genomes, all three light orientations: many commits per batch, beam fronts rewritten
+    # by one lane and sensed by a later one, two lanes rewriting the same front
+    rng = np.random.default_rng(10)
+    gs = np.stack([np.zeros(144, dtype=np.uint8), rng.integers(0, 2, size=144, dtype=np.uint8), genomes["loco_random"]])
+    sizes = [(6, 3), (6, 1), (10, 7), (13, 9), (20, 14), (9, 2)]
+    seeds = [3, 4, 5, 6, 7, 8]
+    orient = np.asarray([[1, 2, 3, 1, 2, 3], [2, 3, 1, 2, 3, 1], [3, 1, 2, 3, 1, 2]], dtype=np.uint8)
+    got, want, cnt = run_pair(ctx, E.LOCO, gs, sizes, seeds, rng_mode, steps=100001, orient=orient, flags=ROUNDS[rounds])
+    check_equal(ctx, E.LOCO, gs, sizes, seeds, got, want, cnt, rng_mode, 100001, orient=orient, flags=ROUNDS[rounds])
+    assert cnt[2] > 0.1 * cnt[0]
+
+
 def test_agg_large_batch_takes_the_throughput_form(ctx, genomes):
     # more chains than 8 per SM: the host picks the "touched lanes only" rounds and 8-warp CTAs; same bits
     gs = np.stack([np.zeros(48, dtype=np.uint8), genomes["agg_evolved"]])

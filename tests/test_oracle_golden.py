@@ -220,3 +220,49 @@ def test_eval_batch_matches_single_envs(genomes):
             r = O.Env(O.AGG, gs[gi], *sizes[t], seed=seeds[t]).simulate()
             assert out[gi, t]["i0"] == r.i0 and out[gi, t]["norm"] == r.norm
     assert cnt[0] == 2 * (37 ** 3 * 2 + 91 ** 3)
+
+
+# ---------------------------------------------------------------- chain dynamics vs the reference's own trajectories --
+# The reference's move stream is unseeded, so its trajectories cannot be reproduced bit for bit — but the
+# lattices it printed after n, n^2 and n^3 steps (misc_scripts/generate_tikz_img_{agg,sep}.py; the genomes are the
+# theory aggregation genome [file suffix _Tho] and the evolved separation genome of genome_sep_compare.py) are samples
+# of the chain the oracle restates.  Over many move seeds from the SAME initial lattice the oracle's distribution of
+# the fitness statistic at each of those step counts must bracket the reference's sample inside its 1st..99th
+# percentile.  (The full-length separation distribution over 256 seeds runs on the GPU — tests/test_gpu_parity.py —
+# whose verification mode is bit-exact to this oracle; here it runs over 48 seeds.)
+def _bracket(samples, ref, what):
+    lo, hi = np.percentile(samples, [1, 99])
+    assert lo <= ref <= hi, "%s: reference %.6g outside the oracle's 1..99 percentile band [%.6g, %.6g]" % (what, ref, lo, hi)
+
+
+def test_agg_trajectory_brackets_reference_snapshots(fixtures, genomes):
+    env = O.Env(O.AGG, genomes["agg_theory"], 13, 9, seed=62813, prob_table=1)
+    ref_edges = []
+    for grid in fixtures["agg_13_9_snapshots"]:
+        env.load_grid(grid)
+        ref_edges.append(env.fitness().i0)
+    assert ref_edges == [395, 399, 515, 717]
+    n, seeds = 271, 256
+    ms = (np.arange(1, seeds + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)).reshape(1, seeds)
+    for steps, ref in zip((n, n * n, n ** 3), ref_edges[1:]):
+        out, _ = O.eval_batch(O.AGG, genomes["agg_theory"], [(13, 9)] * seeds, [62813] * seeds, rng_mode=0, move_seeds=ms,
+                              steps_override=steps, prob_table=1)
+        _bracket(out["i0"].reshape(-1).astype(float), ref, "agg edges after %d steps" % steps)
+
+
+def test_sep_trajectory_brackets_reference_snapshots(fixtures, genomes):
+    env = O.Env(O.SEP, genomes["sep_evolved"], 13, 9, seed=71729, w1=0.65, w2=0.35)
+    ref_fit = []
+    for grid in fixtures["sep_13_9_snapshots"]:
+        env.load_grid(grid)
+        ref_fit.append(float(env.fitness().f))
+    n = 270
+    for steps, ref, seeds in zip((n, n * n, n ** 3), ref_fit[1:], (256, 256, 48)):
+        ms = (np.arange(1, seeds + 1, dtype=np.uint64) * np.uint64(0xD1B54A32D192ED03)).reshape(1, seeds)
+        out, _ = O.eval_batch(O.SEP, genomes["sep_evolved"], [(13, 9)] * seeds, [71729] * seeds, w1=0.65, w2=0.35,
+                              rng_mode=0, move_seeds=ms, steps_override=steps)
+        f = out["f"].reshape(-1).astype(float)
+        if seeds >= 256:
+            _bracket(f, ref, "sep fitness after %d steps" % steps)
+        else:
+            assert f.min() <= ref <= f.max(), (steps, ref, f.min(), f.max())
