@@ -459,3 +459,83 @@ def test_randomised_parity_sweep(ctx):
         kflag = E.F_FORCE_CTA if (rng_mode == E.RNG_FAST and a <= 29 and rng.integers(0, 2)) else 0
         got, want, cnt = run_pair(ctx, beh, gs, [size, size], seeds, rng_mode, steps=steps, move_seeds=ms, orient=orient, flags=kflag)
         check_equal(ctx, beh, gs, [size, size], seeds, got, want, cnt, rng_mode, steps, move_seeds=ms, orient=orient, flags=kflag)
+
+
+# ---------------------------------------------------------------- full-length chains, every behaviour -----------------
+def _oracle_full_chain(args):
+    beh, genome, size, seed, mode, ms, ori = args
+    w1, w2 = W[beh]
+    env = O.Env(beh, genome, *size, seed=seed, w1=w1, w2=w2, rng_mode=mode, move_seed=ms, orientation=ori)
+    env.step(env.sim_duration)
+    r = env.fitness()
+    return (r.i0, r.i1, r.i2, float(r.f)), env.grid(), env.particles(), env.counters()
+
+
+@pytest.mark.parametrize("rng_mode", [E.RNG_VERIFY, E.RNG_FAST])
+def test_full_length_chains_bit_exact_sep_loco_coat(ctx, genomes, rng_mode):
+    # ONE complete n^3 chain per case, final lattice + particle list + integers + counters against the oracle: the late,
+    # low-acceptance regime of separation / locomotion / coating included (the capped-chain tests above stop at 2 % of a
+    # (13,9) chain).  Oracle chains run concurrently (ctypes releases the GIL).
+    from concurrent.futures import ThreadPoolExecutor
+    cases = [(E.SEP, genomes["sep_evolved"], (13, 9), 71729, 1)]
+    cases += [(E.LOCO, genomes["loco_random"], (13, 9), 5, o) for o in (1, 2, 3)]
+    cases += [(E.COAT, genomes["coat_random"], (20, 5, 2), 1, 1), (E.COAT, genomes["coat_random"], (26, 8, 4), 2, 1)]
+    ms = 0xC0FFEE
+    with ThreadPoolExecutor(max_workers=len(cases)) as pool:
+        futs = [pool.submit(_oracle_full_chain, (beh, g, size, seed, rng_mode, ms, ori)) for beh, g, size, seed, ori in cases]
+        for (beh, g, size, seed, ori), fut in zip(cases, futs):
+            w1, w2 = W[beh]
+            got = ctx.eval_batch(beh, g, [size], [seed], w1=w1, w2=w2, rng_mode=rng_mode, flags=E.F_DUMP,
+                                 move_seeds=np.asarray([[ms]], dtype=np.uint64),
+                                 orient=np.asarray([[ori]], dtype=np.uint8) if beh == E.LOCO else None)
+            c = ctx.counters()
+            G, n, dur = E.instance_shape(beh, size)
+            grid, parts = ctx.dump_state(0, G, n)
+            (i0, i1, i2, f), ogrid, oparts, ocnt = fut.result()
+            r = got[0, 0]
+            assert (int(r["i0"]), int(r["i1"]), int(r["i2"])) == (i0, i1, i2), (beh, size)
+            assert abs(float(r["f"]) - f) <= 1e-6 * abs(f)
+            assert (c["attempts"], c["possible"], c["committed"]) == tuple(int(v) for v in ocnt) and c["attempts"] == dur
+            assert np.array_equal(grid, ogrid), "lattice differs: behaviour %d size %r" % (beh, size)
+            assert np.array_equal(parts, oparts), "particle list differs: behaviour %d size %r" % (beh, size)
+
+
+def test_fast_mode_matches_verify_mode_distribution_ks_all_behaviours(ctx, genomes):
+    # north_star: fast-mode (Philox) fitness distributions over >= 1000 seeds must match the reference stream's within a
+    # stated KS tolerance: two-sample KS p > 1e-3 and means within 0.01, 1024 move seeds per mode, FULL n^3 chains, for
+    # aggregation at the reference's own size (13,9) and for separation, coating and locomotion.  (Verification mode is
+    # bit-exact to the oracle's WyRand restatement: tests above.)
+    from scipy.stats import ks_2samp
+    N = 1024
+    ms_a = (np.arange(1, N + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)).reshape(1, N)
+    ms_b = (np.arange(7001, 7001 + N, dtype=np.uint64) * np.uint64(0xD1B54A32D192ED03)).reshape(1, N)
+    cases = [(E.AGG, genomes["agg_evolved"], (13, 9), 62813, "i0"), (E.SEP, genomes["sep_evolved"], (13, 9), 71729, "f"),
+             (E.COAT, genomes["coat_random"], (20, 5, 2), 3, "f"), (E.LOCO, genomes["loco_random"], (13, 9), 5, "f")]
+    for beh, g, size, seed, key in cases:
+        w1, w2 = W[beh]
+        ori = (np.arange(N) % 3 + 1).astype(np.uint8).reshape(1, N) if beh == E.LOCO else None
+        a = ctx.eval_batch(beh, g, [size] * N, [seed] * N, w1=w1, w2=w2, rng_mode=E.RNG_VERIFY, move_seeds=ms_a, orient=ori)
+        b = ctx.eval_batch(beh, g, [size] * N, [seed] * N, w1=w1, w2=w2, rng_mode=E.RNG_FAST, move_seeds=ms_b, orient=ori)
+        res = ks_2samp(a[key].reshape(-1), b[key].reshape(-1))
+        assert res.pvalue > 1e-3, (beh, size, res)
+        assert abs(a["norm"].mean() - b["norm"].mean()) < 0.01, (beh, a["norm"].mean(), b["norm"].mean())
+
+
+def test_sep_full_length_distribution_brackets_reference_snapshot(ctx, fixtures, genomes):
+    # the reference's own (13,9)/71729 lattice after n^3 steps (generate_tikz_img_sep.py) has fitness 0.97621; over 256
+    # move seeds in verification mode (the oracle's stream, bit for bit — four of them re-run on the oracle here) it
+    # must lie inside the 1st..99th percentile of the final fitness (tests/test_oracle_golden.py does n and n^2 on CPU)
+    env = O.Env(O.SEP, genomes["sep_evolved"], 13, 9, seed=71729, w1=0.65, w2=0.35)
+    env.load_grid(fixtures["sep_13_9_snapshots"][3])
+    ref = float(env.fitness().f)
+    assert abs(ref - 0.97620815) < 1e-6
+    N = 256
+    ms = (np.arange(1, N + 1, dtype=np.uint64) * np.uint64(0xD1B54A32D192ED03)).reshape(1, N)
+    got = ctx.eval_batch(E.SEP, genomes["sep_evolved"], [(13, 9)] * N, [71729] * N, w1=0.65, w2=0.35, rng_mode=E.RNG_VERIFY,
+                         move_seeds=ms)
+    f = got["f"].reshape(-1).astype(float)
+    lo, hi = np.percentile(f, [1, 99])
+    assert lo <= ref <= hi, (ref, lo, hi)
+    want, _ = O.eval_batch(O.SEP, genomes["sep_evolved"], [(13, 9)] * 4, [71729] * 4, w1=0.65, w2=0.35, rng_mode=0,
+                           move_seeds=ms[:, :4].copy())
+    assert np.array_equal(got["i0"][0, :4], want["i0"][0]) and np.array_equal(got["i1"][0, :4], want["i1"][0])
