@@ -3,11 +3,15 @@
 
 A "step" is one GA generation's evaluation batch (what base_ga.rs:393-411's nested par_iter does):
 config C2 of BASELINE.json / SURVEY.md §8d — aggregation, pop 50 x sizes {(6,4),(10,7),(13,9)} x seeds 1..5
-= 750 independent chains of n^3 attempts each (6.24e9 attempts).  With --gpus N every rank evaluates its own
-50-genome shard of a 50*N population (weak scaling, no data-path collective; one max/sum reduce for the report).
+= 750 independent chains of n^3 attempts each (6.24e9 attempts).  With --gpus N the population is 50*N genomes
+sharded over the ranks (weak scaling: 50 genomes per GPU; instances are independent, so the chain kernels need no
+collective).
 
   value   attempts/s, inputs resident in HBM, CUDA-event time of the chain kernel on its own stream
-  e2e     the same through sops_eval_batch with HOST buffers (validation + H2D + kernel + D2H + float fitness)
+  e2e     the same through the public sharded call (evosops_b200.sharding.evaluate_sharded over Context.eval_batch):
+          HOST buffers, validation + H2D + kernel + D2H + float fitness on every rank, then ONE NCCL all_gather of the
+          24-byte results so every rank holds the population's fitness table (what base_ga.rs:401-424 reduces)
+  strong_scaling   fixed populations (agg pop 400, sep C3 pop 200) over the N ranks, beside the same population on one GPU
   --impl reference   the CPU oracle (the Rust reference cannot be built here: no cargo) on all host threads,
                      each step a bounded sample (--ref-pop genomes of the 50)
 """
@@ -164,7 +168,30 @@ def workload_config(args):
             % (POP_C2, "".join("(%d,%d)" % s for s in SIZES_C2), args.gran),
             "instances_per_gpu": POP_C2 * len(SIZES_C2) * len(SEEDS_C2), "rng": args.rng,
             "sharding": "population sharded, %d genomes per GPU" % POP_C2,
-            "l2": "flushed between timed steps (256 MiB write); working set is shared-memory resident"}
+            "l2": "flushed between timed steps (256 MiB write); working set is shared-memory resident",
+            "reference_arm_sample": "--impl reference times %d of the %d genomes per step (a rate: attempts/s)" % (args.ref_pop, POP_C2)}
+
+
+def ncu_measured(tag):
+    """Issue-slot utilisation of the chain kernel as ncu measured it on this workload (profiles/r02_ncu_summary.json,
+    written by scripts/ncu_summary.py from a `ncu --set full` capture of this same command)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_summary.json")) as f:
+            return json.load(f).get(tag)
+    except (OSError, ValueError):
+        return None
+
+
+def late_generation_population(rank, gran):
+    """+-1 mutants of the reference's evolved genome (what the GA converges to): the C2 batch shape with few accepted moves."""
+    evo = np.tile(np.asarray(EVOLVED_AGG, dtype=np.uint8), (POP_C2, 1))
+    for g in range(1, POP_C2):
+        st = (GENOME_SEED ^ (0x9E3779B97F4A7C15 * (rank * POP_C2 + g))) & 0xFFFFFFFFFFFFFFFF
+        for _ in range(3):
+            st, z = splitmix64(st)
+            k = z % 48
+            evo[g, k] = min(gran, max(0, int(evo[g, k]) + (1 if (z >> 32) & 1 else -1)))
+    return evo
 
 
 def main():
@@ -176,7 +203,7 @@ def main():
     ap.add_argument("--rng", default="fast", choices=["fast", "verify"])
     ap.add_argument("--gran", type=int, default=10)
     ap.add_argument("--ref-pop", type=int, default=16)
-    ap.add_argument("--no-extra", action="store_true", help="skip the verify-mode and sweep side measurements")
+    ap.add_argument("--no-extra", action="store_true", help="skip the side measurements (other mode, configs C3/C4, sweeps, strong scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -191,6 +218,7 @@ def main():
     import torch
     import torch.distributed as dist
     import evosops_b200 as E
+    from evosops_b200 import sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
@@ -222,15 +250,32 @@ def main():
         dist.all_reduce(t, op=op)
         return float(t.item())
 
+    MAX = dist.ReduceOp.MAX if world > 1 else None
+    SUM = dist.ReduceOp.SUM if world > 1 else None
+
     ctx = E.Context(device_ids=[local])
     mode = E.RNG_FAST if args.rng == "fast" else E.RNG_VERIFY
-    gs = synthetic_genomes(rank * POP_C2, POP_C2, 48, args.gran)
+    P_glob = POP_C2 * world
+    gs_glob = synthetic_genomes(0, P_glob, 48, args.gran)       # genome g depends only on its global index
+    lo, hi = sharding.shard_range(P_glob, world, rank)
+    gs = gs_glob[lo:hi]
     tsz, tsd = trial_list(SIZES_C2, SEEDS_C2)
+    T = len(tsz)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def l2_flush():
         flush.add_(1)
         torch.cuda.synchronize()
+
+    def best_of(reps=3):
+        """device ms of the prepared batch: one warm-up launch, then the best of `reps` (max over ranks each time)"""
+        ctx.launch(); ctx.sync()
+        best = None
+        for _ in range(reps):
+            ctx.launch()
+            ms = reduce(ctx.sync(), MAX)
+            best = ms if best is None else min(best, ms)
+        return best
 
     # ---- device-resident leg: prepare once (H2D), time K launches with CUDA events on the launch stream
     ctx.prepare(E.AGG, gs, tsz, tsd, gran=args.gran, rng_mode=mode)
@@ -247,90 +292,114 @@ def main():
         dev_ms += ctx.sync()
     barrier()
     t_wall1 = time.time()
-    res = ctx.collect()
+    ctx.collect()
     cnt = ctx.counters()
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     attempts_step = float(cnt["attempts"])
     p_poss = cnt["possible"] / cnt["attempts"]
     p_acc = cnt["committed"] / cnt["attempts"]
     launches_step = cnt["launches"]
-    worst_ms = reduce(dev_ms, dist.ReduceOp.MAX if world > 1 else None)
-    total_attempts = reduce(attempts_step, dist.ReduceOp.SUM if world > 1 else None) * args.steps
+    worst_ms = reduce(dev_ms, MAX)
+    total_attempts = reduce(attempts_step, SUM) * args.steps
     value = total_attempts / (worst_ms * 1e-3)
 
-    # ---- end-to-end leg: the public call with host buffers, H2D + D2H inside the timed region
-    for _ in range(1):
-        ctx.eval_batch(E.AGG, gs, tsz, tsd, gran=args.gran, rng_mode=mode)
+    # ---- end-to-end leg: the public sharded call with host buffers; H2D, D2H and the NCCL all_gather of the 24-byte
+    # results are inside the timed region (at N = 1 the gather is a no-op)
+    def evaluate_local(g_shard, ms_shard, _orient):
+        return ctx.eval_batch(E.AGG, g_shard, tsz, tsd, gran=args.gran, rng_mode=mode, move_seeds=ms_shard)
+
+    res = sharding.evaluate_sharded(evaluate_local, gs_glob, T)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = ctx.eval_batch(E.AGG, gs, tsz, tsd, gran=args.gran, rng_mode=mode)
+        res = sharding.evaluate_sharded(evaluate_local, gs_glob, T)
     barrier()
     e2e_s = time.perf_counter() - t0
     cnt2 = ctx.counters()
-    e2e_worst = reduce(e2e_s, dist.ReduceOp.MAX if world > 1 else None)
+    e2e_worst = reduce(e2e_s, MAX)
     e2e_value = total_attempts / e2e_worst
+    assert res.shape == (P_glob, T)
     mean_fitness = float(res["norm"].mean())
+    rows = -(-P_glob // world)
+    comm_bytes = 0 if world == 1 else rows * T * 24 * world       # bytes every rank receives in the all_gather
 
     extra = {}
     sweep_local = None
     if not args.no_extra:
-        # the other RNG mode on the same batch, and a throughput-bound sweep (config 5 style, capped chains)
+        # (every side measurement: one warm-up launch, best of 3, device time, max over ranks)
+        # the other RNG mode on the same batch
         other = E.RNG_VERIFY if mode == E.RNG_FAST else E.RNG_FAST
         ctx.prepare(E.AGG, gs, tsz, tsd, gran=args.gran, rng_mode=other)
-        ctx.launch(); ctx.sync()
-        ctx.launch(); ms_o = ctx.sync()
+        ms_o = best_of()
         ctx.collect()
-        v_o = reduce(attempts_step, dist.ReduceOp.SUM if world > 1 else None) / (reduce(ms_o, dist.ReduceOp.MAX if world > 1 else None) * 1e-3)
-        extra["verify_mode" if other == E.RNG_VERIFY else "fast_mode"] = {"value": v_o, "unit": "attempts/s", "ms_per_step": ms_o}
-        # a late-generation population: +-1 mutants of the reference's evolved genome (what the GA converges to);
-        # same batch shape as the headline, far fewer accepted moves per chain
-        evo = np.tile(np.asarray(EVOLVED_AGG, dtype=np.uint8), (POP_C2, 1))
-        for g in range(1, POP_C2):
-            st = (GENOME_SEED ^ (0x9E3779B97F4A7C15 * (rank * POP_C2 + g))) & 0xFFFFFFFFFFFFFFFF
-            for _ in range(3):
-                st, z = splitmix64(st)
-                k = z % 48
-                evo[g, k] = min(args.gran, max(0, int(evo[g, k]) + (1 if (z >> 32) & 1 else -1)))
-        best = None
-        for kname, kflag in (("warp", 0), ("cta4", E.F_FORCE_CTA)):
-            ctx.prepare(E.AGG, evo, tsz, tsd, gran=args.gran, rng_mode=mode, flags=kflag)
-            ctx.launch(); ctx.sync()
-            ctx.launch(); ms_e = ctx.sync()
-            res_e = ctx.collect()
-            ms_e = reduce(ms_e, dist.ReduceOp.MAX if world > 1 else None)
-            if best is None or ms_e < best[0]:
-                best = (ms_e, kname, float(res_e["norm"].mean()))
-            extra.setdefault("evolved_population", {})["ms_per_step_" + kname] = ms_e
-        v_e = reduce(attempts_step, dist.ReduceOp.SUM if world > 1 else None) / (best[0] * 1e-3)
-        extra["evolved_population"].update({"value": v_e, "unit": "attempts/s", "ms_per_step": best[0], "kernel": best[1],
-                                            "generations_per_s": 1e3 / best[0], "mean_fitness": best[2]})
-        # the same GA generation with a population of 400 on ONE GPU (6000 chains): what a larger population gets
-        big = synthetic_genomes(rank * 400, 400, 48, args.gran)
-        ctx.prepare(E.AGG, big, tsz, tsd, gran=args.gran, rng_mode=mode)
-        ctx.launch(); ms_b = ctx.sync()
-        ctx.collect()
-        cb = ctx.counters()
-        extra["ga_generation_pop400_per_gpu"] = {
-            "value": reduce(float(cb["attempts"]), dist.ReduceOp.SUM if world > 1 else None) /
-                     (reduce(ms_b, dist.ReduceOp.MAX if world > 1 else None) * 1e-3),
-            "unit": "attempts/s", "ms_per_step": ms_b, "instances_per_gpu": 400 * len(tsz)}
+        extra["verify_mode" if other == E.RNG_VERIFY else "fast_mode"] = {
+            "value": reduce(attempts_step, SUM) / (ms_o * 1e-3), "unit": "attempts/s", "ms_per_step": ms_o}
+        # a late-generation population: same batch shape as the headline, far fewer accepted moves per chain
+        evo = late_generation_population(rank, args.gran)
+        ctx.prepare(E.AGG, evo, tsz, tsd, gran=args.gran, rng_mode=mode)
+        ms_e = best_of()
+        res_e = ctx.collect()
+        extra["evolved_population"] = {"value": reduce(attempts_step, SUM) / (ms_e * 1e-3), "unit": "attempts/s", "ms_per_step": ms_e,
+                                       "generations_per_s": 1e3 / ms_e, "mean_fitness": float(res_e["norm"].mean())}
+        # the other behaviours' GA generations (BASELINE configs 3 and 4: pop 200, random genomes), per GPU
+        W = {E.SEP: (0.65, 0.35), E.COAT: (0.65, 0.35), E.LOCO: (0.75, 0.25)}
+        for name, beh, sizes, gseed in (("c3_sep_pop200_13_9", E.SEP, [(13, 9)], 3), ("c4_loco_pop200_13_9", E.LOCO, [(13, 9)], 4),
+                                        ("c4_coat_pop200_20_5_2_26_8_4", E.COAT, [(20, 5, 2), (26, 8, 4)], 5)):
+            gb = np.random.default_rng(gseed + 1000 * rank).integers(0, 11, size=(200, E.GENOME_LEN[beh]), dtype=np.uint8)
+            bsz, bsd = trial_list(sizes, SEEDS_C2)
+            ori = (np.arange(200 * len(bsz)) % 3 + 1).astype(np.uint8) if beh == E.LOCO else None
+            ctx.prepare(beh, gb, bsz, bsd, gran=args.gran, w1=W[beh][0], w2=W[beh][1], rng_mode=mode, orient=ori)
+            ms_b = best_of()
+            ctx.collect()
+            cb = ctx.counters()
+            extra[name] = {"value": reduce(float(cb["attempts"]), SUM) / (ms_b * 1e-3), "unit": "attempts/s", "ms_per_step": ms_b,
+                           "instances_per_gpu": 200 * len(bsz), "p_poss": cb["possible"] / cb["attempts"],
+                           "p_acc": cb["committed"] / cb["attempts"]}
+        # throughput-bound seed sweeps (config 5 style, capped chains): one fixed genome x many seeds
         n_sweep, cap = 50000, 200000
         seeds = list(range(1 + rank * n_sweep, 1 + (rank + 1) * n_sweep))
         for nm, md in (("fast", E.RNG_FAST), ("verify", E.RNG_VERIFY)):
-            # one fixed genome (the reference's evolved aggregation genome) x many seeds
             ctx.prepare(E.AGG, np.asarray(EVOLVED_AGG, dtype=np.uint8).reshape(1, 48), [(13, 9)] * n_sweep, seeds, gran=args.gran,
                         rng_mode=md, steps_override=cap)
-            ctx.launch(); ctx.sync()
-            ctx.launch(); ms_s = ctx.sync()
+            ms_s = best_of()
             ctx.collect()
             cs = ctx.counters()
             if nm == "fast":
                 sweep_local = (ms_s, cs["possible"] / cs["attempts"], cs["committed"] / cs["attempts"], float(cs["attempts"]))
-            tot = reduce(float(n_sweep) * cap, dist.ReduceOp.SUM if world > 1 else None)
-            extra["sweep_13_9_%s" % nm] = {"value": tot / (reduce(ms_s, dist.ReduceOp.MAX if world > 1 else None) * 1e-3),
+            extra["sweep_13_9_%s" % nm] = {"value": reduce(float(n_sweep) * cap, SUM) / (ms_s * 1e-3),
                                            "unit": "attempts/s", "instances_per_gpu": n_sweep, "steps_cap": cap,
                                            "genome": "reference evolved agg genome"}
+        # ---- strong scaling: FIXED populations sharded over the N ranks (device time of the slowest rank), beside the
+        # same population on ONE GPU in the same run (rank 0 alone); at N > 1 rank 0 also checks that the sharded
+        # results are bit-identical to the single-GPU ones
+        strong = {}
+        for name, beh, pop, sizes, w in (("agg_pop400_c2_sizes", E.AGG, 400, SIZES_C2, (0.0, 0.0)),
+                                         ("sep_pop200_c3", E.SEP, 200, [(13, 9)], (0.65, 0.35))):
+            L = E.GENOME_LEN[beh]
+            gfix = synthetic_genomes(0, pop, L, args.gran) if beh == E.AGG else \
+                np.random.default_rng(3).integers(0, 11, size=(pop, L), dtype=np.uint8)
+            ssz, ssd = trial_list(sizes, SEEDS_C2)
+            slo, shi = sharding.shard_range(pop, world, rank)
+            ctx.prepare(beh, gfix[slo:shi], ssz, ssd, gran=args.gran, w1=w[0], w2=w[1], rng_mode=mode)
+            ms_n = best_of()
+            mine = ctx.collect()
+            rec = {"population": pop, "instances": pop * len(ssz), "ms_per_generation": ms_n, "n_gpus": world}
+            if world > 1:
+                ms_1 = 0.0
+                same = 1.0
+                if rank == 0:
+                    ctx.prepare(beh, gfix, ssz, ssd, gran=args.gran, w1=w[0], w2=w[1], rng_mode=mode)
+                    ctx.launch(); ctx.sync(); ctx.launch(); ms_1 = ctx.sync()
+                    full = ctx.collect()
+                    same = 1.0 if np.array_equal(full[slo:shi], mine) else 0.0
+                barrier()
+                ms_1 = reduce(ms_1, MAX)
+                same = reduce(same, dist.ReduceOp.MIN)
+                assert same == 1.0, "sharded results differ from the single-GPU evaluation of the same genomes"
+                rec.update({"ms_per_generation_one_gpu_same_run": ms_1, "speedup": ms_1 / ms_n,
+                            "efficiency": ms_1 / ms_n / world, "rank0_shard_equals_single_gpu": True})
+            strong[name] = rec
+        extra["strong_scaling"] = strong
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -345,31 +414,41 @@ def main():
                 traffic = json.load(f).get("dram_bytes_per_launch")
         except (OSError, ValueError):
             pass
+        issue = issue_view(attempts_step / (k_ms * 1e-3), p_poss, sm_mhz)
         line = {"metric": "particle-move attempts/s", "value": value, "unit": "attempts/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": worst_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32/u64 integer",
                 "data": "synthetic", "config": workload_config(args),
-                "generations_per_s": 1e3 / (worst_ms / args.steps), "population": POP_C2 * world,
+                "generations_per_s": 1e3 / (worst_ms / args.steps), "population": P_glob,
                 "e2e": {"value": e2e_value, "unit": "attempts/s", "h2d_bytes_per_step": cnt2["h2d_bytes"],
-                        "d2h_bytes_per_step": cnt2["d2h_bytes"], "ms_per_step": e2e_worst / args.steps * 1e3},
+                        "d2h_bytes_per_step": cnt2["d2h_bytes"], "ms_per_step": e2e_worst / args.steps * 1e3,
+                        "api": "evosops_b200.sharding.evaluate_sharded(Context.eval_batch)",
+                        "comm": {"collective": "all_gather" if world > 1 else None, "backend": "nccl" if world > 1 else None,
+                                 "bytes_received_per_rank_per_step": comm_bytes}},
                 "gpu_launches": int(launches_step * args.steps),
                 "clocks": clocks,
+                # the path is shared-memory resident: `bound` names the SM-side roofline.  frac/achieved/peak are the
+                # shared-memory bandwidth view the contract's byte formula gives; `binding` is the ceiling that actually
+                # binds (SM issue) and `measured` what ncu saw on this command.
                 "roofline": {"bound": "smem", "achieved": achieved, "peak": peak_smem, "unit": "GB/s",
                              "frac": achieved / peak_smem, "traffic": traffic,
-                             "kernel": "sops_chain_kernel<AGG,RW=1,%s>" % args.rng, "kernel_ms": k_ms,
+                             "kernel": "sops_chain_kernel<AGG,RW=1,%s,parallel rounds>" % args.rng, "kernel_ms": k_ms,
                              "alg_bytes_per_attempt": alg_bytes, "p_poss": p_poss, "p_acc": p_acc,
                              "peak_source": "%s sm_max_mhz x 148 SMs x 128 B/clk shared memory" % peak_src,
-                             "issue": issue_view(attempts_step / (k_ms * 1e-3), p_poss, sm_mhz),
+                             "binding": {"ceiling": "SM issue (thread-instructions)", "frac": issue["frac"], **issue},
+                             "measured": ncu_measured("c2_bench_fast"),
                              "note": "750 chains pulled by 592 warps (one per warp scheduler): dependent-latency bound, the slowest genome's chains set the time; see DESIGN.md"},
                 "mean_fitness": mean_fitness}
         if sweep_local:
             ms_s, pp_s, pa_s, att_s = sweep_local
             ab = 10.0 + 22.3 * pp_s + 18.0 * pa_s
             ach = ab * att_s / (ms_s * 1e-3) / 1e9
+            iv = issue_view(att_s / (ms_s * 1e-3), pp_s, sm_mhz)
             extra["roofline_sweep"] = {"bound": "smem", "achieved": ach, "peak": peak_smem, "unit": "GB/s", "frac": ach / peak_smem,
-                                       "traffic": None, "kernel": "sops_chain_kernel<AGG,RW=1,fast> on the 50000-chain sweep (rank 0)",
+                                       "traffic": None, "kernel": "sops_chain_kernel<AGG,RW=1,fast,serial rounds> on the 50000-chain sweep (rank 0)",
                                        "kernel_ms": ms_s, "alg_bytes_per_attempt": ab, "p_poss": pp_s, "p_acc": pa_s,
-                                       "issue": issue_view(att_s / (ms_s * 1e-3), pp_s, sm_mhz)}
+                                       "binding": {"ceiling": "SM issue (thread-instructions)", "frac": iv["frac"], **iv},
+                                       "measured": ncu_measured("sweep_13_9_fast")}
         line.update(extra)
         if world == 1:
             import multiprocessing
