@@ -334,6 +334,37 @@ def main():
         ctx.collect()
         extra["verify_mode" if other == E.RNG_VERIFY else "fast_mode"] = {
             "value": reduce(attempts_step, SUM) / (ms_o * 1e-3), "unit": "attempts/s", "ms_per_step": ms_o}
+        # ---- strong scaling: FIXED populations sharded over the N ranks (device time of the slowest rank), beside the
+        # same population on ONE GPU in the same run (rank 0 alone); at N > 1 rank 0 also checks that the sharded
+        # results are bit-identical to the single-GPU ones
+        strong = {}
+        for name, beh, pop, sizes, w in (("agg_pop400_c2_sizes", E.AGG, 400, SIZES_C2, (0.0, 0.0)),
+                                         ("sep_pop200_c3", E.SEP, 200, [(13, 9)], (0.65, 0.35))):
+            L = E.GENOME_LEN[beh]
+            gfix = synthetic_genomes(0, pop, L, args.gran) if beh == E.AGG else \
+                np.random.default_rng(3).integers(0, 11, size=(pop, L), dtype=np.uint8)
+            ssz, ssd = trial_list(sizes, SEEDS_C2)
+            slo, shi = sharding.shard_range(pop, world, rank)
+            ctx.prepare(beh, gfix[slo:shi], ssz, ssd, gran=args.gran, w1=w[0], w2=w[1], rng_mode=mode)
+            ms_n = best_of()
+            mine = ctx.collect()
+            rec = {"population": pop, "instances": pop * len(ssz), "ms_per_generation": ms_n, "n_gpus": world}
+            if world > 1:
+                ms_1 = 0.0
+                same = 1.0
+                if rank == 0:
+                    ctx.prepare(beh, gfix, ssz, ssd, gran=args.gran, w1=w[0], w2=w[1], rng_mode=mode)
+                    ctx.launch(); ctx.sync(); ctx.launch(); ms_1 = ctx.sync()
+                    full = ctx.collect()
+                    same = 1.0 if np.array_equal(full[slo:shi], mine) else 0.0
+                barrier()
+                ms_1 = reduce(ms_1, MAX)
+                same = reduce(same, dist.ReduceOp.MIN)
+                assert same == 1.0, "sharded results differ from the single-GPU evaluation of the same genomes"
+                rec.update({"ms_per_generation_one_gpu_same_run": ms_1, "speedup": ms_1 / ms_n,
+                            "efficiency": ms_1 / ms_n / world, "rank0_shard_equals_single_gpu": True})
+            strong[name] = rec
+        extra["strong_scaling"] = strong
         # a late-generation population: same batch shape as the headline, far fewer accepted moves per chain
         evo = late_generation_population(rank, args.gran)
         ctx.prepare(E.AGG, evo, tsz, tsd, gran=args.gran, rng_mode=mode)
@@ -369,37 +400,6 @@ def main():
             extra["sweep_13_9_%s" % nm] = {"value": reduce(float(n_sweep) * cap, SUM) / (ms_s * 1e-3),
                                            "unit": "attempts/s", "instances_per_gpu": n_sweep, "steps_cap": cap,
                                            "genome": "reference evolved agg genome"}
-        # ---- strong scaling: FIXED populations sharded over the N ranks (device time of the slowest rank), beside the
-        # same population on ONE GPU in the same run (rank 0 alone); at N > 1 rank 0 also checks that the sharded
-        # results are bit-identical to the single-GPU ones
-        strong = {}
-        for name, beh, pop, sizes, w in (("agg_pop400_c2_sizes", E.AGG, 400, SIZES_C2, (0.0, 0.0)),
-                                         ("sep_pop200_c3", E.SEP, 200, [(13, 9)], (0.65, 0.35))):
-            L = E.GENOME_LEN[beh]
-            gfix = synthetic_genomes(0, pop, L, args.gran) if beh == E.AGG else \
-                np.random.default_rng(3).integers(0, 11, size=(pop, L), dtype=np.uint8)
-            ssz, ssd = trial_list(sizes, SEEDS_C2)
-            slo, shi = sharding.shard_range(pop, world, rank)
-            ctx.prepare(beh, gfix[slo:shi], ssz, ssd, gran=args.gran, w1=w[0], w2=w[1], rng_mode=mode)
-            ms_n = best_of()
-            mine = ctx.collect()
-            rec = {"population": pop, "instances": pop * len(ssz), "ms_per_generation": ms_n, "n_gpus": world}
-            if world > 1:
-                ms_1 = 0.0
-                same = 1.0
-                if rank == 0:
-                    ctx.prepare(beh, gfix, ssz, ssd, gran=args.gran, w1=w[0], w2=w[1], rng_mode=mode)
-                    ctx.launch(); ctx.sync(); ctx.launch(); ms_1 = ctx.sync()
-                    full = ctx.collect()
-                    same = 1.0 if np.array_equal(full[slo:shi], mine) else 0.0
-                barrier()
-                ms_1 = reduce(ms_1, MAX)
-                same = reduce(same, dist.ReduceOp.MIN)
-                assert same == 1.0, "sharded results differ from the single-GPU evaluation of the same genomes"
-                rec.update({"ms_per_generation_one_gpu_same_run": ms_1, "speedup": ms_1 / ms_n,
-                            "efficiency": ms_1 / ms_n / world, "rank0_shard_equals_single_gpu": True})
-            strong[name] = rec
-        extra["strong_scaling"] = strong
 
     if rank == 0:
         peaks, peak_src = measured_peaks()

@@ -1062,19 +1062,42 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
     } else {
         // Verification mode: the number of draws a step consumes (2 if blocked, 3 if possible) decides
         // where the next step starts in the WyRand chain, so lanes probe both alignments and a
-        // warp-uniform walk over the "possible" ballots picks the real ones.  A commit that flips a later
+        // warp scan over the "possible" ballots picks the real ones.  A commit that flips a later
         // lane's possible-ness invalidates that alignment: the batch is cut there.
+        //
+        // Lane l owns the draws cbase + 2l + 1 (even slot) and cbase + 2l + 2 (odd slot); steps start in lanes 0..29
+        // (a step starting in lane 29's odd slot runs through lane 30), so a batch consumes 60..62 draws.  Every raw
+        // draw is reduced once to a packed word (as particle | as direction << 16 | as probability << 19; bit 31: one of
+        // fastrand's rejection tests fired, p ~ 2e-7) — whichever role the alignment gives it later — and the words of
+        // the NEXT batch are computed while this batch's lattice loads are in flight: they start at cbase + 60, and the
+        // 0..2 draws the batch turns out to consume beyond that are a shift by at most one lane.
+        auto word = [&](uint64_t c) -> uint32_t {
+            const uint64_t r = wy_draw(ms, c);
+            const uint64_t ln = r * (uint64_t)n, l6 = r * 6ull;
+            const uint64_t m1000 = (uint64_t)(uint32_t)r * 1000u;
+            const bool rare = ln < (uint64_t)n || l6 < 6ull || (uint32_t)m1000 < 1000u;
+            return (uint32_t)__umul64hi(r, (uint64_t)n) | ((uint32_t)__umul64hi(r, 6ull) << 16) | ((uint32_t)(m1000 >> 32) << 19) |
+                   (rare ? 0x80000000u : 0u);
+        };
         uint64_t k = 0, cbase = 0;                           // steps retired, thread-local draws consumed
+        uint32_t wE = word(2 * lane + 1), wO = word(2 * lane + 2);
         while (k < steps) {
             const uint64_t rem = steps - k;
-            // raw draws cbase + 2l + 1 (even slot) and cbase + 2l + 2 (odd slot)
             const uint64_t kE = cbase + 2 * lane + 1, kO = kE + 1;
-            const uint64_t rE = wy_draw(ms, kE), rO = wy_draw(ms, kO);
-            const uint64_t nE = __shfl_down_sync(0xffffffffu, rE, 1);
-            const uint32_t nO32 = __shfl_down_sync(0xffffffffu, (uint32_t)rO, 1);
-            // a step starting in the even slot uses (rE, rO, next rE); in the odd slot (rO, next rE, next rO)
-            const uint32_t idxE = wy_mod_u64(rE, n, ms, kE), dE = wy_mod_u64(rO, 6, ms, kO);
-            const uint32_t idxO = wy_mod_u64(rO, n, ms, kO), dO = wy_mod_u64(nE, 6, ms, kO + 1);
+            const uint32_t pN0 = word(kE + 60), pN1 = word(kO + 60);            // the next batch's words (if this one is not cut)
+            const uint32_t nE = __shfl_down_sync(0xffffffffu, wE, 1), nO = __shfl_down_sync(0xffffffffu, wO, 1);
+            // a step starting in the even slot uses (E, O, next E); in the odd slot (O, next E, next O)
+            uint32_t idxE = wE & 0xffffu, dE = (wO >> 16) & 7u, idxO = wO & 0xffffu, dO = (nE >> 16) & 7u;
+            uint32_t pdE = (nE >> 19) & 0x3ffu, pdO = (nO >> 19) & 0x3ffu;
+            if (__any_sync(0xffffffffu, ((wE | wO) >> 31) != 0u)) {
+                // a rejection test fired somewhere in the batch: the exact reductions with fastrand's redraw loops
+                const uint64_t rE = wy_draw(ms, kE), rO = wy_draw(ms, kO);
+                const uint64_t rnE = __shfl_down_sync(0xffffffffu, rE, 1);
+                const uint32_t rnO = __shfl_down_sync(0xffffffffu, (uint32_t)rO, 1);
+                idxE = wy_mod_u64(rE, n, ms, kE); dE = wy_mod_u64(rO, 6, ms, kO);
+                idxO = wy_mod_u64(rO, n, ms, kO); dO = wy_mod_u64(rnE, 6, ms, kO + 1);
+                pdE = wy_mod_1000((uint32_t)rnE, ms, kE + 2); pdO = wy_mod_1000(rnO, ms, kO + 2);
+            }
             const uint32_t PE = __ballot_sync(0xffffffffu, probe_possible<BEH, RW>(L, idxE, dE));
             const uint32_t PO = __ballot_sync(0xffffffffu, probe_possible<BEH, RW>(L, idxO, dO));
             // Which slots start a real step: a blocked step consumes 2 draws, a possible one 3.  Walking lanes in
@@ -1082,42 +1105,49 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
             // slot), S (no step starts here — an odd-slot possible step ran through; the next lane is E again).
             //   E -> possible_E ? O : E      O -> possible_O ? S : O      S -> E
             // Each lane's transition is a map on {E,O,S} (6 bits); the state on entry to lane l is the composition
-            // of the maps of lanes 0..l-1 applied to E: a warp scan over function composition (5 shuffle rounds)
-            // instead of a serial walk.
+            // of the maps of lanes 0..l-1 applied to E: a warp scan over function composition (5 shuffle rounds,
+            // branch-free) instead of a serial walk.
             const uint32_t pe = (PE >> lane) & 1u, po = (PO >> lane) & 1u;
             uint32_t map = pe | ((po ? 2u : 1u) << 2);       // image of E | image of O << 2 | image of S (= E = 0) << 4
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
                 const uint32_t first = __shfl_up_sync(0xffffffffu, map, off);   // composition of the block ending at lane - off
-                if (lane >= (uint32_t)off) {
-                    const uint32_t r0 = (map >> (2u * (first & 3u))) & 3u;
-                    const uint32_t r1 = (map >> (2u * ((first >> 2) & 3u))) & 3u;
-                    const uint32_t r2 = (map >> (2u * ((first >> 4) & 3u))) & 3u;
-                    map = r0 | (r1 << 2) | (r2 << 4);
-                }
+                const uint32_t r0 = (map >> (2u * (first & 3u))) & 3u;
+                const uint32_t r1 = (map >> (2u * ((first >> 2) & 3u))) & 3u;
+                const uint32_t r2 = (map >> (2u * ((first >> 4) & 3u))) & 3u;
+                map = lane >= (uint32_t)off ? (r0 | (r1 << 2) | (r2 << 4)) : map;
             }
             const uint32_t entry = __shfl_up_sync(0xffffffffu, map, 1) & 3u;    // state after lane - 1, started from E
             const uint32_t state = lane == 0 ? 0u : entry;
-            const uint32_t realE = __ballot_sync(0xffffffffu, state == 0u && lane < 31u);
-            const uint32_t realO = __ballot_sync(0xffffffffu, state == 1u && lane < 31u);
-            // draws consumed by lanes 0..30: 62 if the walk leaves lane 30 in E, 63 in O, 64 in S
-            const uint32_t q_end = 62u + (__shfl_sync(0xffffffffu, map, 30) & 3u);
+            const uint32_t realE = __ballot_sync(0xffffffffu, state == 0u && lane < 30u);
+            const uint32_t realO = __ballot_sync(0xffffffffu, state == 1u && lane < 30u);
+            // draws consumed by lanes 0..29: 60 if the walk leaves lane 29 in E, 61 in O, 62 in S
+            const uint32_t shift = __shfl_sync(0xffffffffu, map, 29) & 3u;
             const bool myO = (realO >> lane) & 1u, myE = (realE >> lane) & 1u;
             const uint32_t ord = __popc((realE | realO) & lowmask(lane));
             const bool active = (myE || myO) && (uint64_t)ord < rem;
             Prop p;
             p.idx = myO ? idxO : idxE; p.d = myO ? dO : dE;
             // the probability draw exists only for a possible step; computing it for every lane is harmless
-            p.pd = wy_mod_1000(myO ? nO32 : (uint32_t)nE, ms, (myO ? kO : kE) + 2);
-            if (!active) p.pd = 0xffffffffu;                 // never accepted, also when AGG re-derives after a commit
+            p.pd = myO ? pdO : pdE;
+            if (!active) p.pd = 0xffffffffu;                 // never accepted, also when a commit round re-derives
             evaluate<BEH, RW>(L, g, p);
             if (!active) { p.eff = false; p.poss = false; }
             const uint32_t am = __ballot_sync(0xffffffffu, active);
             const uint32_t R = resolve_batch<BEH, RW, true, ROUNDS>(L, g, lane, active, p, ncommit);
             nposs += (active && p.poss && lane < R) ? 1u : 0u;
             k += __popc(am & lowmask(R));
-            if (R < 32) cbase += 2 * R + __shfl_sync(0xffffffffu, (uint32_t)myO, R);   // the cut lane restarts the next batch
-            else cbase += q_end;
+            if (R < 32) {                                    // the cut lane restarts the next batch: its words are not prefetched
+                cbase += 2 * R + __shfl_sync(0xffffffffu, (uint32_t)myO, R);
+                wE = word(cbase + 2 * lane + 1);
+                wO = word(cbase + 2 * lane + 2);
+            } else {
+                // the prefetched words start at cbase + 60; the batch consumed 60 + shift draws
+                cbase += 60u + shift;
+                const uint32_t a0 = __shfl_down_sync(0xffffffffu, pN0, 1), a1 = __shfl_down_sync(0xffffffffu, pN1, 1);
+                wE = shift == 0u ? pN0 : shift == 1u ? pN1 : a0;
+                wO = shift == 0u ? pN1 : shift == 1u ? a0 : a1;
+            }
         }
     }
     {

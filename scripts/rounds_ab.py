@@ -83,3 +83,8 @@ if "loco" in which:
     for form, fl in (("parallel", E.F_ROUNDS_PARALLEL), ("serial", E.F_ROUNDS_SERIAL)):
         ms, c = timed(E.LOCO, glo, lsz, lsd, fl, w=(0.75, 0.25), orient=ori)
         report("loco pop50 x (13,9) x5 generation", form, ms, c)
+if "pop400" in which:
+    big = bench.synthetic_genomes(0, 400, 48)
+    for form, fl in FORMS:
+        ms, c = timed(E.AGG, big, tsz, tsd, fl)
+        report("agg pop400 generation (6000 chains)", form, ms, c)
