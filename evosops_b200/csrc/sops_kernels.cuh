@@ -1084,7 +1084,6 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
         while (k < steps) {
             const uint64_t rem = steps - k;
             const uint64_t kE = cbase + 2 * lane + 1, kO = kE + 1;
-            const uint32_t pN0 = word(kE + 60), pN1 = word(kO + 60);            // the next batch's words (if this one is not cut)
             const uint32_t nE = __shfl_down_sync(0xffffffffu, wE, 1), nO = __shfl_down_sync(0xffffffffu, wO, 1);
             // a step starting in the even slot uses (E, O, next E); in the odd slot (O, next E, next O)
             uint32_t idxE = wE & 0xffffu, dE = (wO >> 16) & 7u, idxO = wO & 0xffffu, dO = (nE >> 16) & 7u;
@@ -1107,6 +1106,8 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
             // Each lane's transition is a map on {E,O,S} (6 bits); the state on entry to lane l is the composition
             // of the maps of lanes 0..l-1 applied to E: a warp scan over function composition (5 shuffle rounds,
             // branch-free) instead of a serial walk.
+            // (the next batch's words, if this one is not cut: issued here so that they fill the scan's shuffle latencies)
+            const uint32_t pN0 = word(kE + 60), pN1 = word(kO + 60);
             const uint32_t pe = (PE >> lane) & 1u, po = (PO >> lane) & 1u;
             uint32_t map = pe | ((po ? 2u : 1u) << 2);       // image of E | image of O << 2 | image of S (= E = 0) << 4
 #pragma unroll
