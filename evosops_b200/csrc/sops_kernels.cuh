@@ -743,8 +743,7 @@ __device__ __forceinline__ uint32_t resolve_batch_jacobi_sep(const Lat& L, const
         __syncwarp();
         uint32_t P0 = 0, P1 = 0;
         S = 0;
-#pragma unroll 1
-        for (uint32_t b = 0; 4 * b < K; ++b) {
+        auto block = [&](uint32_t b) {
             const uint4 m4 = L.cmp[b];
             const uint32_t mm[4] = {m4.x, m4.y, m4.z, m4.w};
 #pragma unroll
@@ -756,6 +755,12 @@ __device__ __forceinline__ uint32_t resolve_batch_jacobi_sep(const Lat& L, const
                 P1 ^= (m & (1u << 25)) ? dU : 0u;
                 S |= dU;
             }
+        };
+        block(0);                                            // (sentinels past the K-th entry)
+        if (K > 4) {
+            block(1);
+#pragma unroll 1
+            for (uint32_t b = 2; 4 * b < K; ++b) block(b);
         }
         p.U0 = W00 ^ (P0 & 0x1fffffffu);
         p.U1 = W01 ^ (P1 & 0x1fffffffu);
@@ -770,23 +775,30 @@ __device__ __forceinline__ uint32_t resolve_batch_jacobi_sep(const Lat& L, const
     const uint32_t Sb = __ballot_sync(0xffffffffu, active && cut);
     const uint32_t keep = ~Sb & (Sb - 1u);
     const uint32_t C = A & keep;
-    if ((C >> lane) & 1u) {
-        const uint32_t x = (p.tt >> 28) & 3u;
-        const bool swap = (p.tt >> 31) != 0u;
+    {
+        // every lane issues the four atomics (zero masks for the lanes and planes that do not flip): no divergent region
+        const bool mine = (C >> lane) & 1u;
+        const uint32_t x = mine ? (p.tt >> 28) & 3u : 0u;
+        const bool swap = mine && (p.tt >> 31) != 0u;
         uint32_t* ws = const_cast<uint32_t*>(Plane<RW>::word(L.p0, p.s & 0xff, p.s >> 8));
         uint32_t* wt = const_cast<uint32_t*>(Plane<RW>::word(L.p0, p.t & 0xff, p.t >> 8));
         const uint32_t plane1 = (uint32_t)(L.p1 - L.p0);
         const uint32_t ms_ = 1u << ((p.s >> 8) & 31u), mt_ = 1u << ((p.t >> 8) & 31u);
-        if (x & 1u) { atomicXor(ws, ms_); atomicXor(wt, mt_); }
-        if (x & 2u) { atomicXor(ws + plane1, ms_); atomicXor(wt + plane1, mt_); }
+        atomicXor(ws, (x & 1u) ? ms_ : 0u);
+        atomicXor(wt, (x & 1u) ? mt_ : 0u);
+        atomicXor(ws + plane1, (x & 2u) ? ms_ : 0u);
+        atomicXor(wt + plane1, (x & 2u) ? mt_ : 0u);
         const uint32_t is = inv_index<RW>(p.s), it = inv_index<RW>(p.t);
+        const uint32_t partner = L.tab[it];                  // (garbage when the target is empty: used by swaps only)
+        __syncwarp();                                        // every lane has read the map before any lane rewrites it
         if (swap) {
-            const uint32_t partner = L.tab[it];
             L.pos[partner] = (uint16_t)p.s;
             L.tab[is] = (uint16_t)partner;
         }
-        L.pos[p.idx] = (uint16_t)p.t;
-        L.tab[it] = (uint16_t)p.idx;
+        if (mine) {
+            L.pos[p.idx] = (uint16_t)p.t;
+            L.tab[it] = (uint16_t)p.idx;
+        }
     }
     __syncwarp();
     ncommit += (uint32_t)__popc(C);
