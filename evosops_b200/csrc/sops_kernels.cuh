@@ -268,21 +268,19 @@ __device__ __forceinline__ uint4 dirtab_entry(int d) {
 }
 
 // locomotion.rs:260-290 on unpadded coordinates; light[b] = x | y << 8.  Beam id or -1 when the cell is on no beam.
+// Branch-free: the beam through (x, y) is cx*x + cy*y + c0 with (2,-1,0), (-1,2,0), (1,1,-a) for orientation 1, 2, 3, and a
+// cell lies on a beam iff that value is in 0..2a (for orientation 3 that is the reference's  a <= x + y <= 3a).
 __device__ __forceinline__ int loco_beam(uint32_t o, int a, int x, int y) {
-    if (o == 1) { int b = 2 * x - y; return (b >= 0 && b <= 2 * a) ? b : -1; }
-    if (o == 2) { int b = 2 * y - x; return (b >= 0 && b <= 2 * a) ? b : -1; }
-    int sxy = x + y; return (sxy >= a && sxy <= 3 * a) ? sxy - a : -1;
+    const int cx = o == 1 ? 2 : o == 2 ? -1 : 1, cy = o == 1 ? -1 : o == 2 ? 2 : 1, c0 = o == 3 ? -a : 0;
+    const int b = cx * x + cy * y + c0;
+    return (b >= 0 && b <= 2 * a) ? b : -1;
 }
-__device__ __forceinline__ uint32_t loco_sense(const uint16_t* light, uint32_t o, int b, int x, int y) {
-    if (b < 0) return 0;
-    const uint32_t f = light[b];
-    return o == 1 ? (y >= (int)(f >> 8)) : (x >= (int)(f & 0xff));
-}
-
-// sensing against given beam fronts (light[b] = x | y << 8), packed like Prop::aux
+// sensing against given beam fronts (light[b] = x | y << 8), packed like Prop::aux: orientation 1 compares y, the others x
 __device__ __forceinline__ uint32_t loco_aux(uint32_t o, int bs, int bt, uint32_t fs, uint32_t ft, int sx, int sy, int tx, int ty) {
-    const uint32_t cur = bs < 0 ? 0u : (o == 1 ? (uint32_t)(sy >= (int)(fs >> 8)) : (uint32_t)(sx >= (int)(fs & 0xff)));
-    const uint32_t fut = bt < 0 ? 0u : (o == 1 ? (uint32_t)(ty >= (int)(ft >> 8)) : (uint32_t)(tx >= (int)(ft & 0xff)));
+    const int cs = o == 1 ? sy : sx, ct = o == 1 ? ty : tx;
+    const int ls = (int)(o == 1 ? fs >> 8 : fs & 0xffu), lt = (int)(o == 1 ? ft >> 8 : ft & 0xffu);
+    const uint32_t cur = (bs >= 0 && cs >= ls) ? 1u : 0u;
+    const uint32_t fut = (bt >= 0 && ct >= lt) ? 1u : 0u;
     const uint32_t li = (cur == fut) ? 2u : cur;             // (0,1)->0 (1,0)->1 else 2   (locomotion.rs:230-235)
     return li * 48u | ((uint32_t)(bs + 1) << 8) | ((uint32_t)(bt + 1) << 16) | (cur << 24) | (fut << 25);
 }
