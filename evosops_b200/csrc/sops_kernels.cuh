@@ -442,6 +442,14 @@ __device__ __forceinline__ void own_cells_store(uint32_t lane, uint32_t f, uint3
         :: "r"(lane), "r"(f), "r"(a_ws), "r"(v0), "r"(a_wt), "r"(v1), "r"(a_pos), "h"((uint16_t)t) : "memory");
 }
 
+// predicated 16-bit shared-memory store (no divergent region)
+__device__ __forceinline__ void st16_if(bool on, const void* ptr, uint32_t v) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.u32 q, %0, 0;\n\t"
+        "@q st.shared.u16 [%1], %2;\n\t}"
+        :: "r"((uint32_t)on), "r"(smem_addr(ptr)), "h"((uint16_t)v) : "memory");
+}
 // one lane (on != 0) flips one bit in each of two shared-memory words
 __device__ __forceinline__ void own_flip(bool on, uint32_t a0, uint32_t a1, uint32_t m0, uint32_t m1) {
     asm volatile(
@@ -625,7 +633,7 @@ __device__ __forceinline__ uint32_t resolve_batch_jacobi(const Lat& L, const Geo
     const uint32_t below = lowmask(lane);
     const uint32_t K = (uint32_t)__popc(Acur);
     {
-        const uint32_t slot = p.eff ? (uint32_t)__popc(Acur & below) : K + (uint32_t)__popc(~Acur & below);
+        const uint32_t slot = (uint32_t)__popc((p.eff ? Acur : ~Acur) & below) + (p.eff ? 0u : K);
         reinterpret_cast<uint32_t*>(L.cmp)[slot] = p.eff ? desc : 0xffffffffu;
     }
     __syncwarp();
@@ -735,7 +743,7 @@ __device__ __forceinline__ uint32_t resolve_batch_jacobi_sep(const Lat& L, const
         const uint32_t K = (uint32_t)__popc(A);
         {   // descriptor of the current decision: flipped colour bits at 24..25, "swap" at 26
             const uint32_t desc = base_desc | (((p.tt >> 28) & 3u) << 24) | ((p.tt >> 31) << 26);
-            const uint32_t slot = p.eff ? (uint32_t)__popc(A & below) : K + (uint32_t)__popc(~A & below);
+            const uint32_t slot = (uint32_t)__popc((p.eff ? A : ~A) & below) + (p.eff ? 0u : K);
             reinterpret_cast<uint32_t*>(L.cmp)[slot] = p.eff ? desc : 0xffffffffu;
         }
         __syncwarp();
@@ -789,14 +797,10 @@ __device__ __forceinline__ uint32_t resolve_batch_jacobi_sep(const Lat& L, const
         const uint32_t is = inv_index<RW>(p.s), it = inv_index<RW>(p.t);
         const uint32_t partner = L.tab[it];                  // (garbage when the target is empty: used by swaps only)
         __syncwarp();                                        // every lane has read the map before any lane rewrites it
-        if (swap) {
-            L.pos[partner] = (uint16_t)p.s;
-            L.tab[is] = (uint16_t)partner;
-        }
-        if (mine) {
-            L.pos[p.idx] = (uint16_t)p.t;
-            L.tab[it] = (uint16_t)p.idx;
-        }
+        st16_if(swap, L.pos + (swap ? partner : 0u), p.s);
+        st16_if(swap, L.tab + is, partner);
+        st16_if(mine, L.pos + p.idx, p.t);
+        st16_if(mine, L.tab + it, p.idx);
     }
     __syncwarp();
     ncommit += (uint32_t)__popc(C);

@@ -28,5 +28,5 @@ for g in (range(50) if only is None else [only]):
     rows.append((ms, c["possible"] / c["attempts"], c["committed"] / c["attempts"], g))
 rows.sort()
 for ms, pp, pa, g in rows:
-    print("genome %2d  ms=%7.2f  cycles/step=%6.1f  p_poss=%.3f p_acc=%.4f" % (g, ms, ms * 1e-3 * 1.965e9 / steps, pp, pa))
+    print("genome %2d  ms=%7.2f  cycles/step=%6.1f  p_poss=%.3f p_acc=%.4f" % (g, ms, ms * 1e-3 * 1.965e9 / (c["attempts"] / 5), pp, pa))
 print("%s %s: mean ms %.2f  max ms %.2f" % (beh_name, form, np.mean([r[0] for r in rows]), rows[-1][0]))
