@@ -528,6 +528,9 @@ int sops_batch_prepare(sops_ctx* ctx, int behavior, const uint8_t* genomes, uint
                 CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, wpb * 32, grp.smem));
                 if (per_sm < 1) return fail(ctx, SOPS_E_UNSUPPORTED, "instance does not fit in shared memory");
                 uint32_t want = (grp.count + (uint32_t)wpb - 1) / (uint32_t)wpb;
+                // a batch that fits the machine once is spread over ALL SMs (warps pull chains from the work counter, the
+                // few surplus warps exit at once): 1000 chains run as 148 x 7 warps, not 143 x 7 with five SMs idle
+                if (grp.count >= (uint32_t)d.n_sm && want < (uint32_t)d.n_sm) want = (uint32_t)d.n_sm;
                 uint32_t cap = (uint32_t)per_sm * (uint32_t)d.n_sm;
                 grp.blocks = (int)std::min(want, cap);
                 if (one_per_scheduler) grp.blocks = std::min(grp.blocks, d.n_sm);
