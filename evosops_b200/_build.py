@@ -1,4 +1,8 @@
-"""Build libevosops_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+"""Build libevosops_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+Safe under torchrun: every rank may call build(); the compile happens under an exclusive file lock, into a temporary
+file that is renamed over the library only when nvcc has finished, so no process ever dlopens a half-written file."""
+import fcntl
 import os
 import subprocess
 
@@ -30,7 +34,20 @@ def stale():
 
 def build(force=False, verbose=False):
     """Compile the CUDA kernels + C ABI into evosops_b200/libevosops_b200.so; returns its path."""
-    if force or stale():
-        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
-        subprocess.check_call(cmd, cwd=ROOT)
+    if not (force or stale()):
+        return LIB
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or stale():                              # another process may have built it while we waited
+                tmp = LIB + ".tmp.%d" % os.getpid()
+                cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + SOURCES
+                try:
+                    subprocess.check_call(cmd, cwd=ROOT)
+                    os.replace(tmp, LIB)
+                finally:
+                    if os.path.exists(tmp):
+                        os.remove(tmp)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB

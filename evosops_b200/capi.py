@@ -18,7 +18,7 @@ E_ARG, E_GENE, E_SIZE, E_UNSUPPORTED, E_CUDA, E_STATE, E_INIT_REJECT = -1, -2, -
 # every symbol include/evosops.h declares
 SYMBOLS = ["sops_ctx_create", "sops_ctx_destroy", "sops_last_error", "sops_eval_batch", "sops_batch_prepare",
            "sops_batch_launch", "sops_batch_collect", "sops_batch_sync", "sops_batch_counters", "sops_dump_state",
-           "sops_instance_shape", "sops_coat_distance_grid"]
+           "sops_instance_shape", "sops_coat_distance_grid", "sops_ctx_set_trial_steps"]
 
 SIZE_DTYPE = np.dtype([("arena", "<u2"), ("layers", "<u2"), ("coat", "<u2")])
 RESULT_DTYPE = np.dtype([("i0", "<u4"), ("i1", "<u4"), ("i2", "<u4"), ("f", "<f4"), ("norm", "<f8")], align=True)
@@ -60,6 +60,7 @@ def lib():
         L.sops_dump_state.argtypes = [vp, u32, vp, vp]
         L.sops_instance_shape.argtypes = [i32, SopsSize, C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)]
         L.sops_coat_distance_grid.argtypes = [SopsSize, vp]
+        L.sops_ctx_set_trial_steps.argtypes = [vp, vp, u32]
         _LIB = L
     return _LIB
 
@@ -141,6 +142,11 @@ class Context:
         self._check(lib().sops_batch_prepare(self.h, behavior, _ptr(g), P, _ptr(sz), _ptr(sd), T, gran, w1, w2,
                                              rng_mode, _ptr(ms), _ptr(orr), steps_override, flags))
         self._shape = (P, T)
+
+    def set_trial_steps(self, steps):
+        """Per-trial chain lengths for the next prepare / eval_batch (None clears)."""
+        a = None if steps is None else np.ascontiguousarray(np.asarray(steps, dtype=np.uint64))
+        self._check(lib().sops_ctx_set_trial_steps(self.h, _ptr(a), 0 if a is None else a.size))
 
     def launch(self):
         self._check(lib().sops_batch_launch(self.h))

@@ -172,6 +172,7 @@ struct sops_ctx {
     uint16_t prob[16];
     uint64_t totals[6] = {0, 0, 0, 0, 0, 0};
     double last_p_acc[4] = {-1.0, -1.0, -1.0, -1.0};            // committed / attempts of the last collected batch, per behaviour
+    std::vector<uint64_t> trial_steps;                          // sops_ctx_set_trial_steps: consumed by the next prepare
     uint64_t h2d_bytes = 0, d2h_bytes = 0, launches = 0;
 };
 
@@ -304,6 +305,13 @@ void sops_ctx_destroy(sops_ctx* ctx) {
 
 const char* sops_last_error(const sops_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
+int sops_ctx_set_trial_steps(sops_ctx* ctx, const uint64_t* steps, uint32_t T) {
+    if (!ctx) return SOPS_E_ARG;
+    ctx->trial_steps.clear();
+    if (steps && T) ctx->trial_steps.assign(steps, steps + T);
+    return 0;
+}
+
 int sops_instance_shape(int behavior, sops_size size, uint32_t* grid_side, uint32_t* n_particles, uint64_t* sim_duration) {
     Shape s;
     int rc = shape_of(behavior, size, &s);
@@ -403,9 +411,12 @@ int sops_batch_prepare(sops_ctx* ctx, int behavior, const uint8_t* genomes, uint
     memcpy(ctx->h_genomes, genomes, (size_t)P * L);
 
     // cost-sorted instance order (longest chain first), then LPT over devices
+    std::vector<uint64_t> per_trial;
+    per_trial.swap(ctx->trial_steps);                          // consumed by this call
+    if (!per_trial.empty() && per_trial.size() != T) return fail(ctx, SOPS_E_ARG, "sops_ctx_set_trial_steps: length differs from T");
     std::vector<uint64_t> steps_of(T);
     for (uint32_t t = 0; t < T; ++t) {
-        steps_of[t] = (flags & SOPS_F_INIT_ONLY) ? 0 : (steps_override ? steps_override : shp[t].dur);
+        steps_of[t] = (flags & SOPS_F_INIT_ONLY) ? 0 : !per_trial.empty() ? per_trial[t] : (steps_override ? steps_override : shp[t].dur);
     }
     std::vector<uint32_t> trial_order(T);
     for (uint32_t t = 0; t < T; ++t) trial_order[t] = t;

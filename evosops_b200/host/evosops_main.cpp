@@ -200,38 +200,61 @@ int main(int argc, char** argv) {
             const float gw1 = 0.65f, gw2 = 0.35f;                                    // GM uses 0.65 / 0.35 for every behaviour (main.rs:311,366,421)
             HostRng mrng(args.have_ga_seed ? args.ga_seed : now_ns);
             double fitness_tot = 0.0;
+            // every (size, seed) trial of the run (main.rs:244-250), evaluated together: one launch per snapshot stage
+            // (the reference fans the trials out with into_par_iter, main.rs:252-274)
+            std::vector<Trial> trials;
+            std::vector<uint64_t> move_seeds;
+            std::vector<uint8_t> orient;
             for (const auto& sz : sizes)
-                for (uint64_t seed : args.seeds) {                                   // main.rs:244-250
-                    const uint64_t ms = mrng.next();
-                    const auto t0 = std::chrono::steady_clock::now();
-                    if (args.behavior == Agg) {
-                        SOPSEnvironment env = SOPSEnvironment::init_sops_env(ev, all_entries.data(), sz.arena, sz.layers, seed, args.granularity, ms, flags);
-                        env.print_grid(log);
-                        const uint32_t e0 = env.evaluate_fitness();
-                        std::fprintf(log, "Edge Count: %u\n", e0);
-                        std::fprintf(log, "Max Fitness: %llu\n", (unsigned long long)env.get_max_fitness());
-                        std::fprintf(log, "Starting Fitness: %s\n", fmt_display((float)e0 / (float)env.get_max_fitness()).c_str());
-                        const uint32_t edges = args.steps ? env.run_prefix(args.steps).i0 : env.simulate(true, log);
-                        const auto secs = std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - t0).count();
-                        env.print_grid(log);
-                        std::fprintf(log, "Edge Count: %u\n", edges);
-                        const double tf = (double)edges / (double)env.get_max_fitness();
-                        std::fprintf(log, "Fitness: %s\n", fmt_display(tf).c_str());
-                        std::fprintf(log, "Trial Elapsed Time: %llds\n", (long long)secs);
-                        fitness_tot += tf;
-                    } else {
-                        const uint8_t orient = (uint8_t)mrng.inclusive(1, 3);
-                        SOPSFloatEnvironment env(ev, args.behavior, all_entries.data(), sz, seed, args.granularity, gw1, gw2, ms, orient, flags);
-                        env.print_grid(log);
-                        std::fprintf(log, "Starting Fitness: %s\n", fmt_display(env.evaluate_fitness()).c_str());
-                        const float f = args.steps ? env.run_prefix(args.steps).f : env.simulate(true, log);
-                        const auto secs = std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - t0).count();
-                        env.print_grid(log);
-                        std::fprintf(log, "Fitness: %s\n", fmt_display(f).c_str());
-                        std::fprintf(log, "Trial Elapsed Time: %llds\n", (long long)secs);
-                        fitness_tot = (double)((float)fitness_tot + f);              // f32 sum upstream
-                    }
+                for (uint64_t seed : args.seeds) {
+                    trials.push_back(Trial{sz, seed});
+                    move_seeds.push_back(mrng.next());
+                    if (args.behavior != Agg) orient.push_back((uint8_t)mrng.inclusive(1, 3));
                 }
+            const auto t0 = std::chrono::steady_clock::now();
+            const StandaloneRun R = run_standalone(ev, args.behavior, all_entries, trials, args.granularity, gw1, gw2, move_seeds,
+                                                   orient, args.steps, flags);
+            const auto secs = std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - t0).count();
+            const size_t last = R.results.size() - 1;
+            for (size_t t = 0; t < trials.size(); ++t) {
+                const std::vector<uint64_t> at = snapshot_steps(args.behavior, R.n[t]);
+                if (args.behavior == Agg) {
+                    const sops_result& r0 = R.results[0][t];
+                    print_grid(log, R.grids[0][t], R.G[t]);
+                    std::fprintf(log, "Edge Count: %u\n", r0.i0);
+                    std::fprintf(log, "Max Fitness: %llu\n", (unsigned long long)r0.i1);
+                    std::fprintf(log, "Starting Fitness: %s\n", fmt_display((float)r0.i0 / (float)r0.i1).c_str());
+                    for (size_t k = 1; k < last; ++k) {
+                        if (!R.shown[k][t]) continue;
+                        const sops_result& r = R.results[k][t];
+                        print_grid(log, R.grids[k][t], R.G[t]);
+                        std::fprintf(log, "Edge Count: %u\n", r.i0);
+                        std::fprintf(log, "Fitness: %s\n", SOPSEnvironment::fmt_f32((float)r.i0 / (float)r.i1).c_str());
+                    }
+                    const sops_result& rf = R.results[last][t];
+                    print_grid(log, R.grids[last][t], R.G[t]);
+                    std::fprintf(log, "Edge Count: %u\n", rf.i0);
+                    const double tf = (double)rf.i0 / (double)rf.i1;
+                    std::fprintf(log, "Fitness: %s\n", fmt_display(tf).c_str());
+                    std::fprintf(log, "Trial Elapsed Time: %llds\n", (long long)secs);
+                    fitness_tot += tf;
+                } else {
+                    print_grid(log, R.grids[0][t], R.G[t]);
+                    std::fprintf(log, "Starting Fitness: %s\n", fmt_display(R.results[0][t].f).c_str());
+                    for (size_t k = 1; k < last; ++k) {
+                        if (!R.shown[k][t]) continue;
+                        std::fprintf(log, "Step %llu\n", (unsigned long long)at[k - 1]);
+                        print_grid(log, R.grids[k][t], R.G[t]);
+                        std::fprintf(log, "Fitness: %s\n", SOPSEnvironment::fmt_f32(R.results[k][t].f).c_str());
+                    }
+                    const float f = R.results[last][t].f;
+                    print_grid(log, R.grids[last][t], R.G[t]);
+                    std::fprintf(log, "Fitness: %s\n", fmt_display(f).c_str());
+                    std::fprintf(log, "Trial Elapsed Time: %llds\n", (long long)secs);
+                    fitness_tot = (double)((float)fitness_tot + f);                  // f32 sum upstream
+                }
+            }
+            if (args.verbose) std::fprintf(log, "Kernel launches for %zu trials: %llu\n", trials.size(), (unsigned long long)R.launches);
             if (args.behavior == Agg) std::fprintf(log, "Total Fitness: %s\n", fmt_display(fitness_tot).c_str());
             else std::fprintf(log, "Total Fitness: %s\n", fmt_display((float)fitness_tot).c_str());
         }

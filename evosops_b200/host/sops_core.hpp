@@ -10,6 +10,7 @@
 // batched form the GA uses: one eval() per generation instead of the nested par_iter.
 // Rust is not available in this image, so this mirror is C++; the Rust binding is in INTEGRATION.md.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <cstdio>
@@ -41,6 +42,8 @@ public:
     virtual void dump(uint32_t instance, std::vector<uint8_t>& grid, std::vector<uint8_t>& particles, uint32_t G, uint32_t n) = 0;
     // attempts / possible / committed / launches / h2d bytes / d2h bytes of the last eval() (zeros if unknown)
     virtual void counters(uint64_t out[6]) { for (int k = 0; k < 6; ++k) out[k] = 0; }
+    // per-trial chain lengths for the next eval() (sops_ctx_set_trial_steps); false if the evaluator cannot do it
+    virtual bool set_trial_steps(const std::vector<uint64_t>&) { return false; }
 };
 
 class CudaEvaluator : public Evaluator {
@@ -64,6 +67,9 @@ public:
         if (rc) throw std::runtime_error(std::string("sops_eval_batch: ") + sops_last_error(ctx_));
     }
     void counters(uint64_t out[6]) override { if (sops_batch_counters(ctx_, out)) for (int k = 0; k < 6; ++k) out[k] = 0; }
+    bool set_trial_steps(const std::vector<uint64_t>& steps) override {
+        return sops_ctx_set_trial_steps(ctx_, steps.empty() ? nullptr : steps.data(), (uint32_t)steps.size()) == 0;
+    }
     void dump(uint32_t instance, std::vector<uint8_t>& grid, std::vector<uint8_t>& particles, uint32_t G, uint32_t n) override {
         grid.assign((size_t)G * G, 0);
         particles.assign((size_t)n * 3, 0);
@@ -222,5 +228,70 @@ private:
                         uint8_t orient, uint32_t fl)
         : SOPSFloatEnvironment(ev, Loco, g, s, seed, gran, w1, w2, ms, orient, fl) {}
 };
+
+// The standalone genome run (`-e gm`, main.rs:252-274 and its three siblings) over ALL (size, seed) trials at once: the
+// reference runs them under into_par_iter, each trial printing its lattice at step 0, after its snapshot steps and at
+// the end.  Here every snapshot stage is ONE batched evaluation of all trials (per-trial chain lengths: the snapshot
+// steps n, n^2, ... differ per size) — a stage re-runs the counter-based chains from the seeded initial configuration,
+// so a k-step run is the k-step prefix of the full chain.  `stage_steps[s][t]` = moves of trial t in stage s
+// (0 = the initial configuration), `shown[s][t]` = whether the reference prints that snapshot for that trial.
+struct StandaloneRun {
+    std::vector<std::vector<uint64_t>> stage_steps;
+    std::vector<std::vector<uint8_t>> shown;
+    std::vector<std::vector<sops_result>> results;           // [stage][trial]
+    std::vector<std::vector<std::vector<uint8_t>>> grids;    // [stage][trial] lattice in the reference's cell codes
+    std::vector<uint32_t> G, n;
+    std::vector<uint64_t> duration;
+    uint64_t launches = 0;
+};
+inline std::vector<uint64_t> snapshot_steps(int behavior, uint64_t n) {
+    if (behavior == Coat) return {n, n * n, n * n * 20, n * n * 40, n * n * 60, n * n * 70};        // coating.rs:582
+    return {n, n * n};                               // mod.rs:309; separation.rs:833 / locomotion.rs (n^3.. is never reached)
+}
+inline StandaloneRun run_standalone(Evaluator& ev, int behavior, const std::vector<uint8_t>& genome, const std::vector<Trial>& trials,
+                                    uint8_t gran, float w1, float w2, const std::vector<uint64_t>& move_seeds,
+                                    const std::vector<uint8_t>& orient, uint64_t final_steps_override, uint32_t flags) {
+    StandaloneRun R;
+    const size_t T = trials.size();
+    R.G.resize(T); R.n.resize(T); R.duration.resize(T);
+    size_t n_snap = 0;
+    for (size_t t = 0; t < T; ++t) {
+        if (sops_instance_shape(behavior, trials[t].size, &R.G[t], &R.n[t], &R.duration[t])) throw std::invalid_argument("invalid size tuple");
+        n_snap = std::max(n_snap, snapshot_steps(behavior, R.n[t]).size());
+    }
+    const size_t n_stage = n_snap + 2;                       // initial, snapshots, final
+    R.stage_steps.assign(n_stage, std::vector<uint64_t>(T, 0));
+    R.shown.assign(n_stage, std::vector<uint8_t>(T, 1));
+    for (size_t t = 0; t < T; ++t) {
+        const std::vector<uint64_t> at = snapshot_steps(behavior, R.n[t]);
+        const uint64_t total = final_steps_override ? final_steps_override : R.duration[t];
+        for (size_t k = 0; k < n_snap; ++k) {
+            // the snapshot is taken after step index `at` has run, i.e. after at + 1 moves, and only if the chain gets there
+            const bool reached = k < at.size() && at[k] < R.duration[t] && !final_steps_override;
+            R.shown[1 + k][t] = reached ? 1 : 0;
+            R.stage_steps[1 + k][t] = reached ? at[k] + 1 : 0;
+        }
+        R.stage_steps[n_stage - 1][t] = total;
+    }
+    R.results.resize(n_stage);
+    R.grids.assign(n_stage, std::vector<std::vector<uint8_t>>(T));
+    for (size_t s = 0; s < n_stage; ++s) {
+        bool any = s == 0 || s + 1 == n_stage;
+        for (size_t t = 0; t < T; ++t) any = any || R.shown[s][t];
+        if (!any) continue;                                  // no trial prints this snapshot
+        uint32_t fl = flags | SOPS_F_DUMP;
+        if (s == 0) fl |= SOPS_F_INIT_ONLY;
+        else if (!ev.set_trial_steps(R.stage_steps[s])) throw std::runtime_error("evaluator cannot take per-trial chain lengths");
+        ev.eval(behavior, genome, 1, trials, gran, w1, w2, move_seeds, orient, 0, fl, R.results[s]);
+        uint64_t c[6];
+        ev.counters(c);
+        R.launches += c[3];
+        for (size_t t = 0; t < T; ++t) {
+            std::vector<uint8_t> parts;
+            ev.dump((uint32_t)t, R.grids[s][t], parts, R.G[t], R.n[t]);
+        }
+    }
+    return R;
+}
 
 }  // namespace evosops

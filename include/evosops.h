@@ -91,6 +91,12 @@ int sops_eval_batch(sops_ctx* ctx, int behavior, const uint8_t* genomes, uint32_
                     const uint64_t* move_seeds, const uint8_t* loco_orient,
                     uint64_t steps_override, uint32_t flags, sops_result* out);
 
+/* Per-trial chain lengths for the NEXT sops_eval_batch / sops_batch_prepare on this context (copied; consumed by that
+ * call, which must pass the same T): trial t runs steps[t] moves instead of n^3 / steps_override.  The standalone
+ * `-e gm` path uses it to take the reference's snapshots (after n, n^2, ... steps, mod.rs:309, separation.rs:833,
+ * coating.rs:582 — counts that differ per size) of ALL trials with one launch per snapshot.  NULL or T = 0 clears. */
+int sops_ctx_set_trial_steps(sops_ctx* ctx, const uint64_t* steps, uint32_t T);
+
 /* The same call split in three so a caller (bench.py) can time the device part with the inputs
  * already resident in HBM: prepare = validate + H2D, launch = enqueue the chain kernels (async),
  * collect = wait + D2H + float fitness.  launch may be repeated on one prepared batch. */

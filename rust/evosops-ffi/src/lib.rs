@@ -34,6 +34,8 @@ pub const F_INIT_ONLY: u32 = 2;
 pub const F_THEORY_TABLE: u32 = 4;
 pub const F_FORCE_WARP: u32 = 8;
 pub const F_FORCE_CTA: u32 = 16;
+pub const F_ROUNDS_SERIAL: u32 = 32;
+pub const F_ROUNDS_PARALLEL: u32 = 64;
 
 extern "C" {
     fn sops_ctx_create(out: *mut *mut SopsCtx, device_ids: *const c_int, n_dev: c_int) -> c_int;
@@ -45,6 +47,7 @@ extern "C" {
                        move_seeds: *const u64, loco_orient: *const u8,
                        steps_override: u64, flags: u32, out: *mut SopsResult) -> c_int;
     fn sops_batch_counters(ctx: *mut SopsCtx, out: *mut u64) -> c_int;
+    fn sops_ctx_set_trial_steps(ctx: *mut SopsCtx, steps: *const u64, t: u32) -> c_int;
     fn sops_dump_state(ctx: *mut SopsCtx, instance: u32, grid: *mut u8, particles: *mut u8) -> c_int;
     fn sops_instance_shape(behavior: c_int, size: SopsSize, grid_side: *mut u32, n_particles: *mut u32,
                            sim_duration: *mut u64) -> c_int;
@@ -95,6 +98,13 @@ impl Context {
         };
         if rc != 0 { return Err(self.err(rc)); }
         Ok(out)
+    }
+
+    /// Per-trial chain lengths for the next `eval_batch` (the standalone run's snapshots); an empty slice clears.
+    pub fn set_trial_steps(&mut self, steps: &[u64]) -> Result<(), SopsError> {
+        let rc = unsafe { sops_ctx_set_trial_steps(self.raw, if steps.is_empty() { std::ptr::null() } else { steps.as_ptr() }, steps.len() as u32) };
+        if rc != 0 { return Err(self.err(rc)); }
+        Ok(())
     }
 
     /// (attempts, possible, committed, kernel launches, h2d bytes, d2h bytes) of the last batch.

@@ -69,17 +69,50 @@ def test_product_package_never_imports_oracle():
                 assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, f
 
 
+C_TO_RUST = {          # C parameter type (whitespace-normalised) -> the Rust FFI type that has the same ABI
+    "sops_ctx**": "*mut *mut SopsCtx", "sops_ctx*": "*mut SopsCtx", "const sops_ctx*": "*const SopsCtx",
+    "const int*": "*const c_int", "int": "c_int", "const uint8_t*": "*const u8", "uint8_t*": "*mut u8", "uint8_t": "u8",
+    "uint32_t": "u32", "uint32_t*": "*mut u32", "uint64_t": "u64", "uint64_t*": "*mut u64", "const uint64_t*": "*const u64",
+    "float": "f32", "double*": "*mut f64", "const sops_size*": "*const SopsSize", "sops_size": "SopsSize",
+    "sops_result*": "*mut SopsResult", "uint16_t*": "*mut u16", "uint64_t[6]": "*mut u64",
+}
+C_RET = {"int": "c_int", "void": None, "const char*": "*const c_char"}
+
+
+def _c_params(text):
+    out = []
+    for a in text.split(","):
+        a = re.sub(r"/\*.*?\*/", "", a, flags=re.S).strip()
+        m = re.match(r"^(.*?)([A-Za-z_][A-Za-z_0-9]*)(\[\d+\])?$", a)      # type, name, optional array suffix
+        typ = re.sub(r"\s+", " ", m.group(1)).strip().replace(" *", "*") + (m.group(3) or "")
+        out.append(typ)
+    return out
+
+
 def test_rust_binding_source_matches_header():
-    # rust/evosops-ffi cannot be compiled here (no cargo); keep its extern block in sync with the header by text
+    # rust/evosops-ffi cannot be compiled here (no cargo); its extern block is checked against the header by text:
+    # every bound function exists, with the same number of parameters AND the ABI-equivalent type in every position,
+    # and the same return type; flag constants and struct layouts are compared too
     hdr = open(os.path.join(ROOT, "include", "evosops.h")).read()
+    hdr_nc = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     rs = open(os.path.join(ROOT, "rust", "evosops-ffi", "src", "lib.rs")).read()
     ext = rs[rs.index('extern "C" {'):]
     ext = ext[:ext.index("\n}\n")]
-    for name, args in re.findall(r"fn (sops_[a-z_]+)\(([^;]*)\)", ext, flags=re.S):
-        m = re.search(r"\b%s\s*\(([^;]*)\);" % name, hdr, flags=re.S)
+    bound = re.findall(r"fn (sops_[a-z_]+)\(([^;]*?)\)\s*(?:->\s*([^;]+?))?;", ext, flags=re.S)
+    assert len(bound) >= 7
+    for name, args, ret in bound:
+        m = re.search(r"([A-Za-z_][A-Za-z_0-9 ]*\*?)\s*\b%s\s*\(([^;]*)\);" % name, hdr_nc, flags=re.S)
         assert m, name
-        assert len([a for a in args.split(",") if a.strip()]) == len([a for a in m.group(1).split(",") if a.strip()]), name
+        c_ret = re.sub(r"\s+", " ", m.group(1)).strip().replace(" *", "*")
+        assert C_RET[c_ret] == (ret.strip() if ret else None), (name, c_ret, ret)
+        c_types = _c_params(m.group(2))
+        r_types = [re.sub(r"\s+", " ", a.split(":", 1)[1]).strip() for a in args.split(",") if a.strip()]
+        assert len(c_types) == len(r_types), name
+        for k, (ct, rt) in enumerate(zip(c_types, r_types)):
+            assert C_TO_RUST[ct] == rt, "%s parameter %d: C `%s` is bound as Rust `%s`" % (name, k, ct, rt)
     for flag, val in re.findall(r"pub const (F_[A-Z_]+): u32 = (\d+);", rs):
         assert re.search(r"SOPS_%s = %s\b" % (flag, val), hdr), flag
+    for flag, val in re.findall(r"SOPS_(F_[A-Z_]+) = (\d+)", hdr):
+        assert re.search(r"pub const %s: u32 = %s;" % (flag, val), rs), "flag %s missing from the Rust binding" % flag
     assert "pub arena: u16, pub layers: u16, pub coat: u16" in rs
     assert "pub i0: u32, pub i1: u32, pub i2: u32, pub f: f32, pub norm: f64" in rs

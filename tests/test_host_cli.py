@@ -135,6 +135,19 @@ def test_cli_end_to_end_on_gpu(built, tmp_path, fixtures, genomes):
     assert "Edge Count: 395" in log and "Max Fitness: 756" in log and "Starting Fitness: 0.52248675" in log
     final = float(re.findall(r"\nFitness: ([0-9.]+)", log)[-1])
     assert 0.9 < final <= 1.0                                 # the evolved genome aggregates (0.987 +- 0.004)
+    # the standalone run batches its trials: 3 sizes x 5 seeds = 15 trials, one launch per snapshot stage (initial
+    # configuration, after step n, after step n^2, final) instead of one per trial and stage
+    r = subprocess.run([exe, "-b", "agg", "-e", "gm", "-k(6,4)", "-k(10,7)", "-k(13,9)", "-s", "1", "-s", "2", "-s", "3", "-s", "4", "-s", "62813",
+                        "--gran", "10", "--path", str(gfile), "--out", str(out_dir), "--ga-seed", "9", "-v"],
+                       capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr
+    m = re.search(r'Please check: "(Agg_GM_3_sizes_5_trials_gran_10_\d+)" file', r.stdout)
+    log = open(os.path.join(str(out_dir), m.group(1) + ".log")).read()
+    assert int(re.search(r"Kernel launches for 15 trials: (\d+)", log).group(1)) <= 4
+    assert len(re.findall(r"SOPS grid\n", log)) == 15 * 4 and log.count("Trial Elapsed Time:") == 15
+    grids27 = re.findall(r"SOPS grid\n((?: [0-9 ]+\n){27})(?! )", log)
+    last_trial_first = np.asarray([[int(v) for v in row.split()] for row in grids27[-4].strip("\n").split("\n")], dtype=np.uint8)
+    assert np.array_equal(last_trial_first, np.asarray(fixtures["agg_13_9_snapshots"][0], dtype=np.uint8))   # (13,9) / 62813, step 0
     # a short GA: 3 generations, population 6, two sizes x two seeds
     r = subprocess.run([exe, "-b", "sep", "-e", "ga", "-k", "(6,3)", "-k", "(7,4)", "-s", "1", "-s", "2", "--gran", "10", "-p", "6", "-g", "3",
                         "--out", str(out_dir), "--ga-seed", "4"], capture_output=True, text=True, cwd=str(tmp_path))
