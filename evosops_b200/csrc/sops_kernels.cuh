@@ -334,7 +334,8 @@ __device__ __forceinline__ void derive(const Lat& L, const Geo& g, Prop& p) {
     } else if (BEH == LOCO) {
         uint32_t gi = (__popc(p.U0 & p.mB) * 3 + __popc(p.U0 & p.mM)) * 4 + __popc(p.U0 & p.mF);
         gi += p.aux & 0xffu;
-        const uint32_t thr = L.thr[gi];
+        uint32_t thr = L.thr[gi];
+        asm volatile("" : "+r"(thr));                        // (keeps the count / load chain out of a divergent "if possible" region)
         p.poss = (p.U0 & p.tb) == 0u;                        // locomotion.rs:551-568 (p.tb: the one-hot mask described above)
         p.kind = p.poss ? 1u : 0u;
         p.eff = p.poss && p.pd < thr;                        // mod.rs:284-285
@@ -342,7 +343,8 @@ __device__ __forceinline__ void derive(const Lat& L, const Geo& g, Prop& p) {
         const uint32_t b = coat_idx3(__popc(p.U0 & p.mB), __popc(p.U1 & p.mB));
         const uint32_t m = coat_idx2(__popc(p.U0 & p.mM), __popc(p.U1 & p.mM));
         const uint32_t f = coat_idx3(__popc(p.U0 & p.mF), __popc(p.U1 & p.mF));
-        const uint32_t thr = L.thr[(b * 6 + m) * 10 + f];
+        uint32_t thr = L.thr[(b * 6 + m) * 10 + f];
+        asm volatile("" : "+r"(thr));                        // (keeps the count / load chain out of a divergent "if possible" region)
         p.poss = (p.U0 & p.tb) == 0u;                        // coating.rs:515-530 (object cells are in bstat, hence in the mask)
         p.kind = p.poss ? 1u : 0u;
         p.eff = p.poss && p.pd < thr;

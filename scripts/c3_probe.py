@@ -6,6 +6,8 @@ import evosops_b200 as E
 import bench
 ctx = E.Context()
 which = sys.argv[1:] or ["sep", "loco", "coat"]
+cap = [int(w[4:]) for w in which if w.startswith("cap=")]
+cap = cap[0] if cap else 0                      # cap=N: chains stop after N steps (quick ncu captures)
 W = {E.SEP: (0.65, 0.35), E.COAT: (0.65, 0.35), E.LOCO: (0.75, 0.25)}
 for name, beh, sizes, gseed in (("sep", E.SEP, [(13, 9)], 3), ("loco", E.LOCO, [(13, 9)], 4), ("coat", E.COAT, [(20, 5, 2), (26, 8, 4)], 5)):
     if name not in which:
@@ -16,7 +18,7 @@ for name, beh, sizes, gseed in (("sep", E.SEP, [(13, 9)], 3), ("loco", E.LOCO, [
     for mode in (E.RNG_FAST, E.RNG_VERIFY):
         if mode == E.RNG_VERIFY and "verify" not in which:
             continue
-        ctx.prepare(beh, gb, bsz, bsd, w1=W[beh][0], w2=W[beh][1], rng_mode=mode, orient=ori)
+        ctx.prepare(beh, gb, bsz, bsd, w1=W[beh][0], w2=W[beh][1], rng_mode=mode, orient=ori, steps_override=cap)
         ctx.launch(); ctx.sync()
         best = min(ctx.launch() or ctx.sync() for _ in range(3))
         ctx.collect()

@@ -38,7 +38,14 @@ for mode in modes:
     if "c2s" in which:
         probe("agg (13,9) pop50 x5 seeds 2e6 steps", E.AGG, 50, [(13, 9)], [1, 2, 3, 4, 5], mode, steps=2000000, reps=1)
     if "c5s" in which:
-        probe("agg (13,9) 20000 inst x 2e5 steps", E.AGG, 1, [(13, 9)], list(range(1, 20001)), mode, steps=200000, reps=1)
+        # bench.py's seed sweep in small: the reference's evolved genome, serial rounds (what the host picks after a
+        # low-acceptance batch), one launch
+        import bench
+        ev = np.asarray(bench.EVOLVED_AGG, dtype=np.uint8).reshape(1, 48)
+        ctx.prepare(E.AGG, ev, [(13, 9)] * 20000, list(range(1, 20001)), rng_mode=mode, steps_override=200000, flags=E.F_ROUNDS_SERIAL)
+        ctx.launch(); ms = ctx.sync(); ctx.collect(); c = ctx.counters()
+        print("sweep evolved 20000 x (13,9) x 2e5 mode=%d ms=%.2f rate=%.3e p_poss=%.3f p_acc=%.4f" % (
+            mode, ms, c["attempts"] / ms * 1e3, c["possible"] / c["attempts"], c["committed"] / c["attempts"]), flush=True)
     if "c5" in which:
         probe("agg (13,9) 20000 inst x 2e5 steps", E.AGG, 1, [(13, 9)], list(range(1, 20001)), mode, steps=200000)
         probe("agg (13,9) 100000 inst x 1e5 steps", E.AGG, 1, [(13, 9)], list(range(1, 100001)), mode, steps=100000)
