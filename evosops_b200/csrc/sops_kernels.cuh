@@ -696,9 +696,11 @@ __device__ __forceinline__ uint32_t resolve_batch_jacobi(const Lat& L, const Geo
     const uint32_t C = Acur & keep;
     const bool mine = (C >> lane) & 1u;
     {
-        // every lane issues the two atomics (a zero mask for the lanes that do not commit): no divergent region
-        uint32_t* ws = const_cast<uint32_t*>(Plane<RW>::word(L.p0, p.s & 0xff, p.s >> 8));
-        uint32_t* wt = const_cast<uint32_t*>(Plane<RW>::word(L.p0, p.t & 0xff, p.t >> 8));
+        // every lane issues the two atomics: no divergent region.  A lane that does not commit XORs zero into its OWN
+        // word of the warp's scratch list, so the idle lanes never pile up on the few lattice rows (bank conflicts)
+        uint32_t* idle = reinterpret_cast<uint32_t*>(L.cmp) + lane;
+        uint32_t* ws = mine ? const_cast<uint32_t*>(Plane<RW>::word(L.p0, p.s & 0xff, p.s >> 8)) : idle;
+        uint32_t* wt = mine ? const_cast<uint32_t*>(Plane<RW>::word(L.p0, p.t & 0xff, p.t >> 8)) : idle;
         atomicXor(ws, mine ? 1u << ((p.s >> 8) & 31u) : 0u);
         atomicXor(wt, mine ? 1u << ((p.t >> 8) & 31u) : 0u);
         if (mine) L.pos[p.idx] = (uint16_t)p.t;
@@ -788,14 +790,16 @@ __device__ __forceinline__ uint32_t resolve_batch_jacobi_sep(const Lat& L, const
         const bool mine = (C >> lane) & 1u;
         const uint32_t x = mine ? (p.tt >> 28) & 3u : 0u;
         const bool swap = mine && (p.tt >> 31) != 0u;
+        // (a lane / plane that does not flip XORs zero into the lane's own word of the scratch list: no pile-up on the lattice rows)
+        uint32_t* idle = reinterpret_cast<uint32_t*>(L.cmp) + lane;
         uint32_t* ws = const_cast<uint32_t*>(Plane<RW>::word(L.p0, p.s & 0xff, p.s >> 8));
         uint32_t* wt = const_cast<uint32_t*>(Plane<RW>::word(L.p0, p.t & 0xff, p.t >> 8));
         const uint32_t plane1 = (uint32_t)(L.p1 - L.p0);
         const uint32_t ms_ = 1u << ((p.s >> 8) & 31u), mt_ = 1u << ((p.t >> 8) & 31u);
-        atomicXor(ws, (x & 1u) ? ms_ : 0u);
-        atomicXor(wt, (x & 1u) ? mt_ : 0u);
-        atomicXor(ws + plane1, (x & 2u) ? ms_ : 0u);
-        atomicXor(wt + plane1, (x & 2u) ? mt_ : 0u);
+        atomicXor((x & 1u) ? ws : idle, (x & 1u) ? ms_ : 0u);
+        atomicXor((x & 1u) ? wt : idle, (x & 1u) ? mt_ : 0u);
+        atomicXor((x & 2u) ? ws + plane1 : idle, (x & 2u) ? ms_ : 0u);
+        atomicXor((x & 2u) ? wt + plane1 : idle, (x & 2u) ? mt_ : 0u);
         const uint32_t is = inv_index<RW>(p.s), it = inv_index<RW>(p.t);
         const uint32_t partner = L.tab[it];                  // (garbage when the target is empty: used by swaps only)
         __syncwarp();                                        // every lane has read the map before any lane rewrites it
