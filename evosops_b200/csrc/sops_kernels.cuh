@@ -12,15 +12,22 @@
 //   * The Markov chain is strictly sequential, but only ~0.3-15 % of proposals change the state.  The 32
 //     lanes therefore evaluate the next 32 proposals SPECULATIVELY against the current lattice and keep
 //     what they read — the 5x5 bit window around the source, which contains every cell adjacent to source
-//     or target — in a register.  The lowest accepted lane commits; every later lane patches its window
-//     with the two flipped cells (register arithmetic, exact) and re-derives its decision; then the next accepted
-//     lane commits.  All 32 steps retire every batch and the retired sequence is exactly the sequential chain.
-//   * Aggregation decides through a perfect hash of the 8 neighbourhood cells into a per-instance threshold table, and
-//     its commit rounds are straight-line code that commits up to two non-interacting candidates per round
-//     (resolve_batch_agg); the other behaviours re-derive only lanes whose window changed (resolve_batch).
+//     or target — in a register.  What the sequential chain would have shown lane l is that window XOR the moves of
+//     the accepted lanes before l.
+//   * Parallel commit rounds (resolve_batch_jacobi, ..._sep): that is a fixed point over the lanes.  The accepted moves
+//     are compacted into a per-warp list, every later lane fetches each move's exact patch of its window from a small
+//     look-up table, re-derives, the accepted set is voted again, changed lanes are toggled in or out, and at the fixed
+//     point all accepted lanes commit at once (shared-memory atomics).  A lane that proposed a particle an earlier lane
+//     moves cuts the batch (the next batch starts there).  Serial rounds (resolve_batch): the lowest accepted lane
+//     commits, later lanes patch their window arithmetically and only touched lanes re-derive — fewer instructions
+//     when at most one lane of a batch accepts.  ROUNDS is a template parameter; both give the sequential chain's bits.
+//   * Aggregation decides through a perfect hash of the 8 neighbourhood cells into a per-instance threshold table.
 //   * Both RNG modes are counter based: fast = Philox2x32-10 keyed per step; verify = the WyRand
 //     double chain, whose draw count per step (2 or 3) depends on the state — resolved per batch by a
-//     warp scan over the lanes' alignment-automaton transition maps.
+//     warp scan over the lanes' alignment-automaton transition maps; draws are reduced once to packed words and
+//     prefetched one batch ahead.
+//   * Hot loops are written without per-lane branches around loads: ptxas makes those divergent regions, and one costs
+//     a lone warp ~60 cycles.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
