@@ -515,19 +515,25 @@ int sops_batch_prepare(sops_ctx* ctx, int behavior, const uint8_t* genomes, uint
                 // launch geometry: spread few instances over all SMs, otherwise fill the machine with
                 // 8-warp CTAs that pull instances from a work counter
                 kernel_fn fn = kernel_for(behavior, grp.rw, rng_mode, grp.rounds);
+                // How many warps per SM?  The list is cost-sorted and a GA batch is skewed (chain length goes with n^3), and a
+                // chain is a dependent instruction stream that slows down with every other chain on its warp scheduler.  So
+                // no more warps are resident than it takes to start every LONG chain (at least half the longest) at once,
+                // rounded up to whole schedulers; the shorter chains are pulled as warps free up.  C2 (250 long of 750): one
+                // warp per scheduler; coating pop 200 (1000 long of 2000): 8 per SM, 13 % faster than 16; aggregation pop 400
+                // (2000 long of 6000): 16 per SM, 25 % faster than 24.  Equal-cost batches (seed sweeps) fill the machine.
                 int wpb = 8;
-                bool one_per_scheduler = false;
-                if (grp.count <= 8u * (uint32_t)d.n_sm) {
-                    wpb = (int)((grp.count + (uint32_t)d.n_sm - 1) / (uint32_t)d.n_sm);
-                    if (wpb > 4) {
-                        // A chain is a dependent instruction stream; two chains on one warp scheduler slow each other
-                        // down.  The list is cost-sorted (longest first): if 4 warps per SM — one per scheduler —
-                        // pulling from it finish no later than everything resident at once, run it that way.
-                        double total = 0, longest = 0;
-                        for (uint32_t q : cls[c]) { const double st = (double)steps_of[q % T] + 1.0; total += st; longest = std::max(longest, st); }
-                        const double resident = longest * (1.0 + 0.25 * ((double)wpb / 4.0 - 1.0));
-                        const double pulled = std::max(longest, total / (4.0 * (double)d.n_sm));
-                        if (pulled <= resident) { wpb = 4; one_per_scheduler = true; }
+                uint32_t resident_cap = 0;                      // CTAs; 0 = whatever fits
+                {
+                    double longest = 0;
+                    for (uint32_t q : cls[c]) longest = std::max(longest, (double)steps_of[q % T]);
+                    uint32_t n_long = 0;
+                    for (uint32_t q : cls[c]) if ((double)steps_of[q % T] * 2.0 >= longest) ++n_long;
+                    uint32_t W = (n_long + (uint32_t)d.n_sm - 1) / (uint32_t)d.n_sm;      // warps per SM to hold the long chains
+                    W = std::max(4u, (W + 3u) & ~3u);
+                    if (grp.count < 4u * (uint32_t)d.n_sm) W = std::max(1u, (grp.count + (uint32_t)d.n_sm - 1) / (uint32_t)d.n_sm);
+                    if (W <= 16u) {
+                        wpb = (int)std::min(W, 8u);
+                        resident_cap = (uint32_t)d.n_sm * ((W + (uint32_t)wpb - 1) / (uint32_t)wpb);
                     }
                 }
                 if (wpb < 1) wpb = 1;
@@ -543,8 +549,8 @@ int sops_batch_prepare(sops_ctx* ctx, int behavior, const uint8_t* genomes, uint
                 // few surplus warps exit at once): 1000 chains run as 148 x 7 warps, not 143 x 7 with five SMs idle
                 if (grp.count >= (uint32_t)d.n_sm && want < (uint32_t)d.n_sm) want = (uint32_t)d.n_sm;
                 uint32_t cap = (uint32_t)per_sm * (uint32_t)d.n_sm;
+                if (resident_cap) cap = std::min(cap, resident_cap);
                 grp.blocks = (int)std::min(want, cap);
-                if (one_per_scheduler) grp.blocks = std::min(grp.blocks, d.n_sm);
             }
             d.groups.push_back(grp);
         }
