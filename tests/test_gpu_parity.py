@@ -183,7 +183,8 @@ def test_loco_commit_rounds_under_heavy_acceptance(ctx, genomes, rng_mode, round
 
 
 def test_agg_large_batch_takes_the_throughput_form(ctx, genomes):
-    # more chains than 8 per SM: the host picks the "touched lanes only" rounds and 8-warp CTAs; same bits
+    # more chains than the machine holds at once (2400 equal-cost chains): 8-warp CTAs at full occupancy pulling from
+    # the work counter, and — after a first low-acceptance batch — the serial rounds the host predicts for it; same bits
     gs = np.stack([np.zeros(48, dtype=np.uint8), genomes["agg_evolved"]])
     seeds = list(range(1, 1201))
     sizes = [(6, 3)] * len(seeds)
