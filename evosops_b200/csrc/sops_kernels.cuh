@@ -1165,10 +1165,21 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
             const uint32_t R = resolve_batch<BEH, RW, true, ROUNDS>(L, g, lane, active, p, ncommit);
             nposs += (active && p.poss && lane < R) ? 1u : 0u;
             k += __popc(am & lowmask(R));
-            if (R < 32) {                                    // the cut lane restarts the next batch: its words are not prefetched
-                cbase += 2 * R + __shfl_sync(0xffffffffu, (uint32_t)myO, R);
-                wE = word(cbase + 2 * lane + 1);
-                wO = word(cbase + 2 * lane + 2);
+            if (R < 32) {
+                // the cut lane restarts the next batch in the slot it started in: the draw stream moves down by 2R (+1) slots.
+                // Its words are already here — this batch's (draws cbase + 1 .. 64) and the prefetched ones (from cbase + 61):
+                // even-slot word m of the stream is wE of lane m, or pN0 of lane m - 30 from m = 30 on; same for odd slots
+                // (cuts happen in lanes <= 29, so m <= 61 and the prefetched lanes suffice)
+                const uint32_t o = __shfl_sync(0xffffffffu, (uint32_t)myO, R);
+                cbase += 2 * R + o;
+                const uint32_t m = R + lane, m1 = m + 1;
+                const uint32_t ea = __shfl_sync(0xffffffffu, wE, m), eb = __shfl_sync(0xffffffffu, pN0, m - 30);
+                const uint32_t oa = __shfl_sync(0xffffffffu, wO, m), ob = __shfl_sync(0xffffffffu, pN1, m - 30);
+                const uint32_t fa = __shfl_sync(0xffffffffu, wE, m1), fb = __shfl_sync(0xffffffffu, pN0, m1 - 30);
+                // (lane 31's words may be stale after an uncut batch's one-lane shift: the prefetched ones take over from m = 30)
+                const uint32_t Es = m < 30 ? ea : eb, Os = m < 30 ? oa : ob, Es1 = m1 < 30 ? fa : fb;
+                wE = o ? Os : Es;
+                wO = o ? Es1 : Os;
             } else {
                 // the prefetched words start at cbase + 60; the batch consumed 60 + shift draws
                 cbase += 60u + shift;
