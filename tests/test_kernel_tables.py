@@ -92,3 +92,25 @@ def test_pair_commit_criterion(tables):
             for dr, dc in DIRS:
                 for cell in ((orow, ocol), (orow + dr, ocol + dc)):      # the other move's two cells, relative to my source
                     assert max(abs(cell[0]), abs(cell[1])) > 2
+
+
+def test_patch_lookup_table_and_index_arithmetic(tables):
+    # the parallel commit rounds fetch "what lane f's move flips in lane l's window" from a table by one packed
+    # subtraction, one validity mask and one byte dot product: for every relative position (incl. far ones, where the packed
+    # subtraction borrows) and direction the result must be exactly the two flipped cells clipped to the 5x5 window, bit 31
+    # iff the mover's source is lane l's source (same particle), bit 30 iff its target is, and nothing for a lane that is
+    # not earlier in the batch
+    ws = tables["ws"]
+    assert len(tables["plut"]) == 21 * 21 * 6 * 3
+    for orow, ocol, d, lane_f, lane_l, word in tables["plut"]:
+        want = 0
+        if lane_f < lane_l:
+            src, tgt = (orow, ocol), (orow + DIRS[d][0], ocol + DIRS[d][1])
+            for cell in (src, tgt):
+                if -2 <= cell[0] <= 2 and -2 <= cell[1] <= 2:
+                    want ^= 1 << (ws * (cell[0] + 2) + (cell[1] + 2))
+            if src == (0, 0):
+                want |= 1 << 31
+            if tgt == (0, 0):
+                want |= 1 << 30
+        assert word == want, (orow, ocol, d, lane_f, lane_l, hex(word), hex(want))

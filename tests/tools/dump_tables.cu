@@ -32,6 +32,33 @@ int main() {
         std::printf("%s[%d, %d, %d, %d, %d]", first ? "" : ", ", r1, c1, r2, c2, near_sources(a, b) ? 1 : 0);
         first = false;
     }
+    std::printf("], \"plut\": [");
+    // The parallel commit rounds' patch look-up (plut_fetch in the header), restated on the host with the header's own
+    // table (plut_entry), byte weights (SOPS_PLUT_DP4A) and validity test: v = m + (0x0303 - s_l) with m = s_f | d << 16 |
+    // lane_f << 24; valid iff ((v | v + 0x0101) & 0xF8F8) == 0; entry address = dot(bytes(v), bytes(weights)); counted only
+    // for an earlier lane (m < lane_l << 24).  Dumped: [row offset, col offset, d, lane_f, lane_l, patch word or 0].
+    first = true;
+    const uint32_t wts = SOPS_PLUT_DP4A;
+    for (int orow = -38; orow <= 38; orow += (orow >= -9 && orow < 9) ? 1 : 29)
+        for (int ocol = -48; ocol <= 48; ocol += (ocol >= -9 && ocol < 9) ? 1 : 39)
+            for (int d = 0; d < 6; ++d)
+                for (int pair = 0; pair < 3; ++pair) {
+                    const uint32_t lane_f = pair == 0 ? 3u : pair == 1 ? 17u : 31u, lane_l = pair == 0 ? 9u : pair == 1 ? 17u : 0u;
+                    const uint32_t sl = centre;
+                    const uint32_t sf = (uint32_t)(40 + orow) | ((uint32_t)(50 + ocol) << 8);
+                    const uint32_t m = sf | ((uint32_t)d << 16) | (lane_f << 24), bias = 0x0303u - sl, mykey = lane_l << 24;
+                    const uint32_t v = m + bias;
+                    const uint32_t z = (v | (v + 0x0101u)) & 0xF8F8u;
+                    uint32_t word = 0;
+                    if (z == 0u && m < mykey) {
+                        uint32_t addr = 0;
+                        for (int b = 0; b < 4; ++b) addr += ((v >> (8 * b)) & 0xffu) * ((wts >> (8 * b)) & 0xffu);
+                        const uint32_t k = addr / 4u;
+                        word = k < SOPS_PLUT_WORDS ? plut_entry((int)(k / 49u), (int)((k % 49u) / 7u), (int)(k % 7u)) : 0xdeadbeefu;
+                    }
+                    std::printf("%s[%d, %d, %d, %u, %u, %u]", first ? "" : ", ", orow, ocol, d, lane_f, lane_l, word);
+                    first = false;
+                }
     std::printf("]}\n");
     return 0;
 }
