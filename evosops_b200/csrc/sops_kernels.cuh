@@ -147,8 +147,6 @@ static_assert(magic_is_perfect(0) && magic_is_perfect(1) && magic_is_perfect(2) 
               magic_is_perfect(4) && magic_is_perfect(5), "window hash must be a bijection for every direction");
 #define SOPS_AGG_TAB_WORDS (6u * 256u / 2u)                  // u16 thresholds, [direction][hash]
 
-// index of the most significant set bit (one FLO; 0xffffffff for 0) — for a one-hot mask, the index of its bit
-__device__ __forceinline__ uint32_t bfind32(uint32_t x) { uint32_t r; asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x)); return r; }
 __device__ __forceinline__ uint32_t lowmask(uint32_t r) { return r >= 32 ? 0xffffffffu : ((1u << r) - 1u); }
 
 // ------------------------------------------------------------------------------ bit planes ------
@@ -214,14 +212,6 @@ __host__ __device__ __forceinline__ uint32_t win25_patch(uint32_t x, uint32_t de
 #endif
     const uint32_t mv = 1u << (iv & 31u), mw = 1u << (iw & 31u);
     return (vin ? mv : 0u) ^ (win_ ? mw : 0u);
-}
-
-// Two packed cells (row | col << 8) within Chebyshev distance 3 of each other?  Never misses a near pair; the byte
-// arithmetic can wrap for row distances >= 250 (largest arenas only) and then answers "near", the safe side.  Two moves whose SOURCES are farther apart than that cannot interact:
-// a move flips cells within distance 1 of its source, a decision reads cells within distance 2 of its source.
-__host__ __device__ __forceinline__ bool near_sources(uint32_t a, uint32_t b) {
-    const uint32_t dd = a - b + 0x0303u;                     // fields 0..6 when |drow|, |dcol| <= 3
-    return ((dd | (dd + 0x0101u)) & 0xFFFFF8F8u) == 0u;
 }
 
 // Patch look-up table for the parallel commit rounds (resolve_batch_jacobi): what a committed move s_f -> s_f + D[d]
@@ -430,27 +420,6 @@ __device__ __forceinline__ bool probe_possible(const Lat& L, uint32_t idx, uint3
 }
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-// the committing lane's own lattice update, in two halves so the loads can be issued early
-// (w0 / w1 are written by lane f only; the other lanes' values are never stored anywhere)
-__device__ __forceinline__ void own_cells_load(uint32_t lane, uint32_t f, uint32_t a_ws, uint32_t a_wt, uint32_t& w0, uint32_t& w1) {
-    asm volatile(
-        "{\n\t.reg .pred q;\n\t"
-        "setp.eq.u32 q, %2, %3;\n\t"
-        "@q ld.shared.b32 %0, [%4];\n\t"
-        "@q ld.shared.b32 %1, [%5];\n\t}"
-        : "=r"(w0), "=r"(w1) : "r"(lane), "r"(f), "r"(a_ws), "r"(a_wt) : "memory");
-}
-__device__ __forceinline__ void own_cells_store(uint32_t lane, uint32_t f, uint32_t a_ws, uint32_t a_wt, uint32_t a_pos,
-                                                uint32_t v0, uint32_t v1, uint32_t t) {
-    asm volatile(
-        "{\n\t.reg .pred q;\n\t"
-        "setp.eq.u32 q, %0, %1;\n\t"
-        "@q st.shared.b32 [%2], %3;\n\t"
-        "@q st.shared.b32 [%4], %5;\n\t"
-        "@q st.shared.u16 [%6], %7;\n\t}"
-        :: "r"(lane), "r"(f), "r"(a_ws), "r"(v0), "r"(a_wt), "r"(v1), "r"(a_pos), "h"((uint16_t)t) : "memory");
-}
-
 // predicated 16-bit shared-memory store (no divergent region)
 __device__ __forceinline__ void st16_if(bool on, const void* ptr, uint32_t v) {
     asm volatile(

@@ -72,28 +72,6 @@ def test_window_patch_flips_exactly_the_cells_inside_the_window(tables):
         assert mask == want, (orow, ocol, d, mask, want)
 
 
-def test_pair_commit_criterion(tables):
-    # (1) the packed-arithmetic test never misses a near pair (that would be a wrong result); it is exactly
-    # "Chebyshev distance <= 3" except for row distances >= 250, where the byte arithmetic wraps and it errs on the
-    # safe side (claims "near": the two moves are then simply committed one after the other)
-    assert len(tables["near"]) == 17 ** 4
-    for r1, c1, r2, c2, near in tables["near"]:
-        truly = max(abs(r1 - r2), abs(c1 - c2)) <= 3
-        if truly:
-            assert near == 1, (r1, c1, r2, c2)
-        elif abs(r1 - r2) < 250:
-            assert near == 0, (r1, c1, r2, c2)
-    # (2) and beyond that distance two moves cannot interact: a move flips its source and a cell next to it, a
-    # decision (and the "same particle" test) reads only the 5x5 window around its own source
-    for orow in range(-6, 7):
-        for ocol in range(-6, 7):
-            if max(abs(orow), abs(ocol)) <= 3:
-                continue
-            for dr, dc in DIRS:
-                for cell in ((orow, ocol), (orow + dr, ocol + dc)):      # the other move's two cells, relative to my source
-                    assert max(abs(cell[0]), abs(cell[1])) > 2
-
-
 def test_patch_lookup_table_and_index_arithmetic(tables):
     # the parallel commit rounds fetch "what lane f's move flips in lane l's window" from a table by one packed
     # subtraction, one validity mask and one byte dot product: for every relative position (incl. far ones, where the packed

@@ -23,15 +23,6 @@ int main() {
                 std::printf("%s[%d, %d, %d, %u]", first ? "" : ", ", orow, ocol, d, win25_patch(sf, tf - sf, org));
                 first = false;
             }
-    std::printf("], \"near\": [");
-    // near_sources over a grid of padded cells incl. the extremes of the u8 coordinate range
-    const int probe[] = {2, 3, 5, 6, 7, 9, 10, 40, 41, 43, 44, 45, 128, 250, 253, 254, 255};
-    first = true;
-    for (int r1 : probe) for (int c1 : probe) for (int r2 : probe) for (int c2 : probe) {
-        const uint32_t a = (uint32_t)r1 | ((uint32_t)c1 << 8), b = (uint32_t)r2 | ((uint32_t)c2 << 8);
-        std::printf("%s[%d, %d, %d, %d, %d]", first ? "" : ", ", r1, c1, r2, c2, near_sources(a, b) ? 1 : 0);
-        first = false;
-    }
     std::printf("], \"plut\": [");
     // The parallel commit rounds' patch look-up (plut_fetch in the header), restated on the host with the header's own
     // table (plut_entry), byte weights (SOPS_PLUT_DP4A) and validity test: v = m + (0x0303 - s_l) with m = s_f | d << 16 |
