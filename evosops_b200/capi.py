@@ -10,7 +10,7 @@ from . import _build
 AGG, SEP, COAT, LOCO = 0, 1, 2, 3
 RNG_VERIFY, RNG_FAST = 0, 1
 F_DUMP, F_INIT_ONLY, F_THEORY_TABLE, F_FORCE_WARP, F_FORCE_CTA = 1, 2, 4, 8, 16
-F_ROUNDS_SERIAL, F_ROUNDS_PARALLEL = 32, 64
+F_ROUNDS_SERIAL, F_ROUNDS_PARALLEL, F_ROUNDS_ADAPTIVE = 32, 64, 128
 GENOME_LEN = {AGG: 48, SEP: 600, COAT: 600, LOCO: 144}
 GENOME_SHAPE = {AGG: (4, 3, 4), SEP: (10, 6, 10), COAT: (10, 6, 10), LOCO: (3, 4, 3, 4)}
 E_ARG, E_GENE, E_SIZE, E_UNSUPPORTED, E_CUDA, E_STATE, E_INIT_REJECT = -1, -2, -3, -4, -5, -6, -7

@@ -217,8 +217,17 @@ kernel_fn pick_sep_narrow(int rw, int mode) {
     if (rw == 1) return mode == 0 ? sops::sops_chain_kernel<sops::SEP, 1, 0, ROUNDS> : sops::sops_chain_kernel<sops::SEP, 1, 1, ROUNDS>;
     return mode == 0 ? sops::sops_chain_kernel<sops::SEP, 2, 0, ROUNDS> : sops::sops_chain_kernel<sops::SEP, 2, 1, ROUNDS>;
 }
+// adaptive rounds: aggregation in fast mode only (the one behaviour whose calm chains gain from them)
+bool has_adaptive_rounds(int beh, int mode) { return beh == SOPS_AGG && mode == SOPS_RNG_FAST; }
+kernel_fn pick_adaptive(int rw) {
+    if (rw == 1) return sops::sops_chain_kernel<sops::AGG, 1, 1, sops::ROUNDS_ADAPTIVE>;
+    if (rw == 2) return sops::sops_chain_kernel<sops::AGG, 2, 1, sops::ROUNDS_ADAPTIVE>;
+    if (rw == 4) return sops::sops_chain_kernel<sops::AGG, 4, 1, sops::ROUNDS_ADAPTIVE>;
+    return sops::sops_chain_kernel<sops::AGG, 8, 1, sops::ROUNDS_ADAPTIVE>;
+}
 kernel_fn kernel_for(int beh, int rw, int mode, int rounds) {
-    const bool par = rounds == sops::ROUNDS_PARALLEL && has_parallel_rounds(beh, rw);
+    if (rounds == sops::ROUNDS_ADAPTIVE && has_adaptive_rounds(beh, mode)) return pick_adaptive(rw);
+    const bool par = rounds != sops::ROUNDS_SERIAL && has_parallel_rounds(beh, rw);
     switch (beh) {
     case SOPS_AGG: return par ? pick_kernel<sops::AGG, sops::ROUNDS_PARALLEL>(rw, mode) : pick_kernel<sops::AGG, sops::ROUNDS_SERIAL>(rw, mode);
     case SOPS_SEP: return par ? pick_sep_narrow<sops::ROUNDS_PARALLEL>(rw, mode) : pick_kernel<sops::SEP, sops::ROUNDS_SERIAL>(rw, mode);
@@ -242,7 +251,7 @@ void layout_group(Group& g, int beh, uint32_t max_pg, uint32_t max_n) {
     g.off_aux = off; if (beh == SOPS_LOCO) off += SOPS_LOCO_AUX_WORDS;
     g.off_tab = off; if (beh == SOPS_AGG) off += SOPS_AGG_TAB_WORDS;
     g.inv_words = 0;
-    if (beh == SOPS_SEP && g.rounds == sops::ROUNDS_PARALLEL) {   // cell -> particle map, u16 per cell, 32 * rw cells per row
+    if (beh == SOPS_SEP && g.rounds != sops::ROUNDS_SERIAL) {     // cell -> particle map, u16 per cell, 32 * rw cells per row
         g.inv_words = (max_pg * 32u * (uint32_t)g.rw + 1u) / 2u;
         off += g.inv_words;
     }
@@ -487,15 +496,36 @@ int sops_batch_prepare(sops_ctx* ctx, int behavior, const uint8_t* genomes, uint
             // kernel choice: one warp per chain, unless the caller asks for the 4-warp CTA-per-chain variant
             // (fast mode only; it pays when few chains with very low acceptance run, i.e. late GA generations)
             grp.cta_w = (rng_mode == SOPS_RNG_FAST && (flags & SOPS_F_FORCE_CTA) && !(flags & SOPS_F_FORCE_WARP) && grp.rw <= 2) ? 4 : 0;
+            // How many warps per SM?  The list is cost-sorted and a GA batch is skewed (chain length goes with n^3), and a
+            // chain is a dependent instruction stream that slows down with every other chain on its warp scheduler.  So
+            // no more warps are resident than it takes to start every LONG chain (at least half the longest) at once,
+            // rounded up to whole schedulers; the shorter chains are pulled as warps free up.  C2 (250 long of 750): one
+            // warp per scheduler; coating pop 200 (1000 long of 2000): 8 per SM, 13 % faster than 16; aggregation pop 400
+            // (2000 long of 6000): 16 per SM, 25 % faster than 24.  Equal-cost batches (seed sweeps) fill the machine.
+            uint32_t W;                                         // resident warps per SM this batch asks for
+            {
+                double longest = 0;
+                for (uint32_t q : cls[c]) longest = std::max(longest, (double)steps_of[q % T]);
+                uint32_t n_long = 0;
+                for (uint32_t q : cls[c]) if ((double)steps_of[q % T] * 2.0 >= longest) ++n_long;
+                W = (n_long + (uint32_t)d.n_sm - 1) / (uint32_t)d.n_sm;               // warps per SM to hold the long chains
+                W = std::max(4u, (W + 3u) & ~3u);
+                if (grp.count < 4u * (uint32_t)d.n_sm) W = std::max(1u, (grp.count + (uint32_t)d.n_sm - 1) / (uint32_t)d.n_sm);
+            }
             // commit rounds of the warp kernel: all accepted lanes at once where the behaviour has that form (the caller
-            // may force either form; the bits are the same)
+            // may force a form; the bits are the same)
             grp.rounds = has_parallel_rounds(behavior, grp.rw) ? sops::ROUNDS_PARALLEL : sops::ROUNDS_SERIAL;
             // aggregation chains that accept little (a converged GA population, seed sweeps of an evolved genome) run
             // 7-10 % faster through the serial form; the acceptance rate of this context's previous aggregation batch is
             // the predictor (unknown: parallel)
             if (behavior == SOPS_AGG && ctx->last_p_acc[SOPS_AGG] >= 0.0 && ctx->last_p_acc[SOPS_AGG] < 0.02) grp.rounds = sops::ROUNDS_SERIAL;
+            // ... and when every chain has a warp scheduler to itself (a GA generation), each chain picks its form itself
+            if (has_adaptive_rounds(behavior, rng_mode) && W <= 4u) grp.rounds = sops::ROUNDS_ADAPTIVE;
             if (flags & SOPS_F_ROUNDS_SERIAL) grp.rounds = sops::ROUNDS_SERIAL;
             if ((flags & SOPS_F_ROUNDS_PARALLEL) && has_parallel_rounds(behavior, grp.rw)) grp.rounds = sops::ROUNDS_PARALLEL;
+            if (flags & SOPS_F_ROUNDS_ADAPTIVE)
+                grp.rounds = has_adaptive_rounds(behavior, rng_mode) ? sops::ROUNDS_ADAPTIVE
+                           : has_parallel_rounds(behavior, grp.rw) ? sops::ROUNDS_PARALLEL : sops::ROUNDS_SERIAL;
             if (grp.cta_w) grp.rounds = sops::ROUNDS_SERIAL;
             layout_group(grp, behavior, max_pg, max_n);
             grp.dump_off = dump_words;
@@ -515,26 +545,11 @@ int sops_batch_prepare(sops_ctx* ctx, int behavior, const uint8_t* genomes, uint
                 // launch geometry: spread few instances over all SMs, otherwise fill the machine with
                 // 8-warp CTAs that pull instances from a work counter
                 kernel_fn fn = kernel_for(behavior, grp.rw, rng_mode, grp.rounds);
-                // How many warps per SM?  The list is cost-sorted and a GA batch is skewed (chain length goes with n^3), and a
-                // chain is a dependent instruction stream that slows down with every other chain on its warp scheduler.  So
-                // no more warps are resident than it takes to start every LONG chain (at least half the longest) at once,
-                // rounded up to whole schedulers; the shorter chains are pulled as warps free up.  C2 (250 long of 750): one
-                // warp per scheduler; coating pop 200 (1000 long of 2000): 8 per SM, 13 % faster than 16; aggregation pop 400
-                // (2000 long of 6000): 16 per SM, 25 % faster than 24.  Equal-cost batches (seed sweeps) fill the machine.
                 int wpb = 8;
                 uint32_t resident_cap = 0;                      // CTAs; 0 = whatever fits
-                {
-                    double longest = 0;
-                    for (uint32_t q : cls[c]) longest = std::max(longest, (double)steps_of[q % T]);
-                    uint32_t n_long = 0;
-                    for (uint32_t q : cls[c]) if ((double)steps_of[q % T] * 2.0 >= longest) ++n_long;
-                    uint32_t W = (n_long + (uint32_t)d.n_sm - 1) / (uint32_t)d.n_sm;      // warps per SM to hold the long chains
-                    W = std::max(4u, (W + 3u) & ~3u);
-                    if (grp.count < 4u * (uint32_t)d.n_sm) W = std::max(1u, (grp.count + (uint32_t)d.n_sm - 1) / (uint32_t)d.n_sm);
-                    if (W <= 16u) {
-                        wpb = (int)std::min(W, 8u);
-                        resident_cap = (uint32_t)d.n_sm * ((W + (uint32_t)wpb - 1) / (uint32_t)wpb);
-                    }
+                if (W <= 16u) {
+                    wpb = (int)std::min(W, 8u);
+                    resident_cap = (uint32_t)d.n_sm * ((W + (uint32_t)wpb - 1) / (uint32_t)wpb);
                 }
                 if (wpb < 1) wpb = 1;
                 while (wpb > 1 && smem_per_warp * (size_t)wpb + 1024 > 227u * 1024u) wpb /= 2;   // largest arenas: fewer warps per CTA

@@ -34,13 +34,29 @@
 
 #include "sops_rng.cuh"
 
+// ROUNDS_ADAPTIVE: batches evaluated side by side while a chain is calm, and the switching thresholds (see run_instance)
+#ifndef SOPS_WIDE_N
+#define SOPS_WIDE_N 3
+#endif
+#ifndef SOPS_WIDE_HOT1
+#define SOPS_WIDE_HOT1 6            // calm -> hot: commits in one wide iteration (32 N steps)
+#endif
+#ifndef SOPS_WIDE_HOT2
+#define SOPS_WIDE_HOT2 9            // ... or in two consecutive wide iterations
+#endif
+#ifndef SOPS_WIDE_CALM
+#define SOPS_WIDE_CALM 16           // hot -> calm: running mean of commits per batch x 16 falls below this
+#endif
+
 namespace sops {
 
 enum { AGG = 0, SEP = 1, COAT = 2, LOCO = 3 };
 enum { MODE_VERIFY = 0, MODE_FAST = 1 };
 // commit-round form of the warp kernel: all accepted lanes at once (fixed-point patch rounds; aggregation, coating) or
 // one commit per round with re-derivation of the lanes whose window changed (every behaviour)
-enum { ROUNDS_PARALLEL = 0, ROUNDS_SERIAL = 1 };
+// ROUNDS_ADAPTIVE (fast mode, chains that have a warp scheduler to themselves): every chain switches, on its own running
+// acceptance rate, between the parallel rounds and serial rounds over SOPS_WIDE_N batches evaluated side by side
+enum { ROUNDS_PARALLEL = 0, ROUNDS_SERIAL = 1, ROUNDS_ADAPTIVE = 2 };
 
 struct Instance {                   // 40 bytes, built on the host, sorted by cost (longest first)
     uint64_t seed;                  // init seed (StdRng::seed_from_u64)
@@ -446,9 +462,11 @@ __device__ __forceinline__ void own_flip(bool on, uint32_t a0, uint32_t a1, uint
 // Lane f flips its two cells (fire-and-forget shared reductions) and rewrites its position.  Every lane then
 // patches its register window with the flipped cells; a lane whose window really changed re-derives, a
 // lane that proposed the moved particle itself (or, LOCO, that senses a rewritten beam) re-reads the lattice.
-template <int BEH, int RW>
+// NLATER: later[0 .. NLATER-1] are further proposals of every lane that come after ALL of p's in chain order (the batches
+// evaluated side by side with this one, resolve_batch_wide): each is repaired like a later lane's.
+template <int BEH, int RW, int NLATER>
 __device__ __forceinline__ void commit_and_repair(const Lat& L, const Geo& g, uint32_t lane, uint32_t f, uint32_t sf, uint32_t ttf,
-                                                  bool active, Prop& p) {
+                                                  bool active, Prop& p, Prop* later) {
     const uint32_t tf = ttf & 0xffffu;
     uint32_t x = 1;                                          // plane bits flipped at both cells
     uint32_t wrote = 0;                                      // LOCO: rewritten beams (+1), 0 = none
@@ -538,10 +556,61 @@ __device__ __forceinline__ void commit_and_repair(const Lat& L, const Geo& g, ui
         if (mine) L.pos[p.idx] = (uint16_t)tf;
         __syncwarp();
     }
-    if (active && lane > f && (dU != 0u || reread)) {
-        if (reread) evaluate<BEH, RW>(L, g, p);
-        else derive<BEH>(L, g, p);
+    if (NLATER == 0 || BEH != AGG) {
+        if (active && lane > f && (dU != 0u || reread)) {
+            if (reread) evaluate<BEH, RW>(L, g, p);
+            else derive<BEH>(L, g, p);
+        }
     }
+    bool rr[NLATER > 0 ? NLATER : 1];
+    bool any_rr = reread && lane > f;
+#pragma unroll
+    for (int j = 0; j < NLATER; ++j) {
+        Prop& q = later[j];
+        const uint32_t dU2 = win25_patch(sf, tf - sf, q.s - 0x0202u);
+        bool reread2 = (q.s == sf);
+        if (BEH == SEP) {
+            if (x & 1) q.U0 ^= dU2;
+            if (x & 2) q.U1 ^= dU2;
+            reread2 |= (q.s == tf);
+        } else {
+            q.U0 ^= dU2;
+            if (BEH == LOCO && wrote) {
+                const uint32_t b1 = wrote & 0xff, b2 = wrote >> 8;
+                const uint32_t bs = (q.aux >> 8) & 0xff, bt = (q.aux >> 16) & 0xff;
+                reread2 |= (b1 && (bs == b1 || bt == b1)) || (b2 && (bs == b2 || bt == b2));
+            }
+        }
+        rr[j] = reread2;
+        any_rr = any_rr || reread2;
+        if (BEH != AGG && (dU2 != 0u || reread2)) {
+            if (reread2) evaluate<BEH, RW>(L, g, q);
+            else derive<BEH>(L, g, q);
+        }
+    }
+    if (NLATER > 0 && BEH == AGG) {
+        // Aggregation's decision is one multiply and one load: everything later in chain order is re-derived without a
+        // branch (a divergent region per proposal costs more than the loads); only a lane that proposed the moved particle
+        // again re-reads the lattice.
+        {
+            Prop t = p;
+            derive<BEH>(L, g, t);
+            if (lane > f) { p.poss = t.poss; p.kind = t.kind; p.eff = t.eff; }
+        }
+#pragma unroll
+        for (int j = 0; j < NLATER; ++j) derive<BEH>(L, g, later[j]);
+        if (any_rr) {
+            if (reread && lane > f) evaluate<BEH, RW>(L, g, p);
+#pragma unroll
+            for (int j = 0; j < NLATER; ++j)
+                if (rr[j]) evaluate<BEH, RW>(L, g, later[j]);
+        }
+    }
+}
+template <int BEH, int RW>
+__device__ __forceinline__ void commit_and_repair(const Lat& L, const Geo& g, uint32_t lane, uint32_t f, uint32_t sf, uint32_t ttf,
+                                                  bool active, Prop& p) {
+    commit_and_repair<BEH, RW, 0>(L, g, lane, f, sf, ttf, active, p, nullptr);
 }
 
 // --- parallel commit rounds (aggregation, coating) --------------------------------------------------------------
@@ -795,8 +864,8 @@ __device__ __forceinline__ uint32_t resolve_batch_jacobi_sep(const Lat& L, const
 // the batch is cut at that lane (returned bound R; lanes >= R are not retired).  ncommit is warp-uniform.
 template <int BEH, int RW, bool VERIFY, int ROUNDS>
 __device__ __forceinline__ uint32_t resolve_batch(const Lat& L, const Geo& g, uint32_t lane, bool active, Prop& p, uint32_t& ncommit) {
-    if (ROUNDS == ROUNDS_PARALLEL && BEH == SEP) return resolve_batch_jacobi_sep<RW, VERIFY>(L, g, lane, active, p, ncommit);
-    if (ROUNDS == ROUNDS_PARALLEL) return resolve_batch_jacobi<BEH, RW, VERIFY>(L, g, lane, active, p, ncommit);
+    if (ROUNDS != ROUNDS_SERIAL && BEH == SEP) return resolve_batch_jacobi_sep<RW, VERIFY>(L, g, lane, active, p, ncommit);
+    if (ROUNDS != ROUNDS_SERIAL) return resolve_batch_jacobi<BEH, RW, VERIFY>(L, g, lane, active, p, ncommit);
     uint32_t R = 32;
     for (;;) {
         uint32_t A = __ballot_sync(0xffffffffu, p.eff);
@@ -815,6 +884,26 @@ __device__ __forceinline__ uint32_t resolve_batch(const Lat& L, const Geo& g, ui
         }
     }
     return R;
+}
+
+// Serial rounds over N batches evaluated side by side against the same lattice (fast mode, full batches): chain order is
+// batch 0's lanes, then batch 1's, ...  A commit of batch i repairs the proposals of the batches after it too (every lane of
+// those is later).  N times the independent work per warp instruction slot for a chain that rarely commits.
+template <int BEH, int RW, int N, int I = 0>
+__device__ __forceinline__ void resolve_batch_wide(const Lat& L, const Geo& g, uint32_t lane, Prop* b, uint32_t& ncommit) {
+    if constexpr (I < N) {
+        for (;;) {
+            const uint32_t A = __ballot_sync(0xffffffffu, b[I].eff);
+            if (!A) break;
+            const uint32_t f = __ffs(A) - 1;
+            const uint32_t sf = __shfl_sync(0xffffffffu, b[I].s, f);
+            const uint32_t ttf = __shfl_sync(0xffffffffu, b[I].tt, f);
+            commit_and_repair<BEH, RW, N - 1 - I>(L, g, lane, f, sf, ttf, true, b[I], b + I + 1);
+            b[I].eff = b[I].eff && lane != f;
+            ++ncommit;
+        }
+        resolve_batch_wide<BEH, RW, N, I + 1>(L, g, lane, b, ncommit);
+    }
 }
 
 // --- initial configuration ---------------------------------------------------------------------------
@@ -1033,7 +1122,16 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
         Prop cur;
         uint32_t curw = draw((uint64_t)lane);
         uint64_t k = 0;                                      // steps retired
-        while (k + 32 <= steps) {
+        // ROUNDS_ADAPTIVE: a chain that rarely commits gains nothing from the parallel rounds, and a lone warp leaves most
+        // of its scheduler's issue slots empty waiting on one batch's loads.  While the chain is calm, N batches (32 N steps)
+        // are evaluated side by side against the same lattice — N times the independent work — and resolved in chain order
+        // by serial rounds (resolve_batch_wide: a commit repairs every later proposal of all N batches).  The chain
+        // switches on its own commit counts: calm -> hot when a wide iteration commits >= SOPS_WIDE_HOT1 times (or two in
+        // a row >= SOPS_WIDE_HOT2), hot -> calm when the running mean of commits per batch (x 16) falls below
+        // SOPS_WIDE_CALM.  Either form retires the sequential chain's steps, so the bits do not depend on the switching.
+        constexpr bool ADAPT = ROUNDS == ROUNDS_ADAPTIVE;
+        constexpr int N = ADAPT ? SOPS_WIDE_N : 1;
+        auto narrow_batch = [&]() {
             const uint32_t nxtw = draw(k + 32 + lane);
             unpack(curw, cur);
             evaluate<BEH, RW>(L, g, cur);
@@ -1041,7 +1139,54 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
             nposs += (cur.poss && lane < R) ? 1u : 0u;
             curw = R == 32 ? nxtw : realign(curw, nxtw, R);
             k += R;
+        };
+        if (ADAPT) {
+            bool calm = false, calm_next = false;
+            uint32_t ema = 2u * SOPS_WIDE_CALM;              // running mean of commits per batch x 16
+            while (k + 32 * N <= steps) {                    // (the chain's last steps go through the plain loop below)
+                if (calm) {
+                    Prop b[N];
+                    uint32_t w[N];
+                    w[0] = curw;
+#pragma unroll
+                    for (int i = 1; i < N; ++i) w[i] = draw(k + 32 * i + lane);
+                    uint32_t prev = 0;
+                    do {
+                        uint32_t nw[N];
+#pragma unroll
+                        for (int i = 0; i < N; ++i) nw[i] = draw(k + 32 * (N + i) + lane);
+#pragma unroll
+                        for (int i = 0; i < N; ++i) unpack(w[i], b[i]);
+#pragma unroll
+                        for (int i = 0; i < N; ++i) evaluate<BEH, RW>(L, g, b[i]);
+                        bool anyeff = false;
+#pragma unroll
+                        for (int i = 0; i < N; ++i) anyeff = anyeff || b[i].eff;
+                        const uint32_t c0 = ncommit;
+                        if (__any_sync(0xffffffffu, anyeff)) resolve_batch_wide<BEH, RW, N>(L, g, lane, b, ncommit);
+#pragma unroll
+                        for (int i = 0; i < N; ++i) { nposs += b[i].poss ? 1u : 0u; w[i] = nw[i]; }
+                        k += 32 * N;
+                        const uint32_t c = ncommit - c0;
+                        if (c >= SOPS_WIDE_HOT1 || c + prev >= SOPS_WIDE_HOT2) calm = false;
+                        prev = c;
+                    } while (calm && k + 32 * N <= steps);
+                    curw = w[0];
+                    calm_next = false;
+                    ema = 2u * SOPS_WIDE_CALM;
+                } else {
+                    do {
+                        const uint32_t c0 = ncommit;
+                        narrow_batch();
+                        // (the decision lags one batch: the loop branch never waits for this batch's commit count)
+                        calm = calm_next;
+                        ema = ema - (ema >> 3) + 2u * (ncommit - c0);
+                        calm_next = ema < SOPS_WIDE_CALM;
+                    } while (!calm && k + 32 * N <= steps);
+                }
+            }
         }
+        while (k + 32 <= steps) narrow_batch();
         while (k < steps) {
             const uint32_t tail = (uint32_t)(steps - k);     // 1..31
             const bool active = lane < tail;
@@ -1199,7 +1344,7 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
 #define SOPS_MIN_BLOCKS 1
 #endif
 template <int BEH, int RW, int MODE, int ROUNDS>
-__global__ void __launch_bounds__(256, BEH == AGG ? 3 : SOPS_MIN_BLOCKS) sops_chain_kernel(const KParams P) {
+__global__ void __launch_bounds__(256, (BEH == AGG && ROUNDS != ROUNDS_ADAPTIVE) ? 3 : SOPS_MIN_BLOCKS) sops_chain_kernel(const KParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint4 s_dirtab[8];
     __shared__ uint32_t s_plut[SOPS_PLUT_WORDS];

@@ -36,6 +36,7 @@ pub const F_FORCE_WARP: u32 = 8;
 pub const F_FORCE_CTA: u32 = 16;
 pub const F_ROUNDS_SERIAL: u32 = 32;
 pub const F_ROUNDS_PARALLEL: u32 = 64;
+pub const F_ROUNDS_ADAPTIVE: u32 = 128;
 
 extern "C" {
     fn sops_ctx_create(out: *mut *mut SopsCtx, device_ids: *const c_int, n_dev: c_int) -> c_int;

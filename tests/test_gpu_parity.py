@@ -121,10 +121,10 @@ def test_agg_many_seeds_short_chains(ctx, genomes, rng_mode, kflag):
     check_equal(ctx, E.AGG, gs, sizes, seeds, got, want, cnt, rng_mode, 300000, move_seeds=ms, dump_every=3, flags=kflag)
 
 
-ROUNDS = {"parallel": E.F_ROUNDS_PARALLEL, "serial": E.F_ROUNDS_SERIAL}
+ROUNDS = {"parallel": E.F_ROUNDS_PARALLEL, "serial": E.F_ROUNDS_SERIAL, "adaptive": E.F_ROUNDS_ADAPTIVE}
 
 
-@pytest.mark.parametrize("rounds", ["parallel", "serial"])
+@pytest.mark.parametrize("rounds", ["parallel", "serial", "adaptive"])
 @pytest.mark.parametrize("rng_mode", [E.RNG_VERIFY, E.RNG_FAST])
 def test_agg_commit_rounds_under_heavy_acceptance(ctx, genomes, rng_mode, rounds):
     # genomes that accept (almost) every possible move: many candidates per 32-step batch, so the commit rounds run
@@ -139,6 +139,29 @@ def test_agg_commit_rounds_under_heavy_acceptance(ctx, genomes, rng_mode, rounds
     got, want, cnt = run_pair(ctx, E.AGG, gs, sizes, seeds, rng_mode, steps=120001, flags=ROUNDS[rounds])
     check_equal(ctx, E.AGG, gs, sizes, seeds, got, want, cnt, rng_mode, 120001, flags=ROUNDS[rounds])
     assert cnt[2] > 0.1 * cnt[0]                              # the batch really is acceptance-heavy
+
+
+@pytest.mark.parametrize("gene_range", [(0, 11), (2, 11), (3, 11), (4, 11), (0, 6), (0, 2)], ids=str)
+def test_agg_adaptive_rounds_switch_between_forms(ctx, genomes, gene_range):
+    # Adaptive rounds (fast mode): a chain runs three batches side by side through serial rounds while it is calm and one
+    # batch through the parallel rounds while it is hot, switching on its own commit counts.  Genomes from calm (the
+    # reference's evolved genome, ~0.3 % accepted) over the switching region (genes 2..10, 3..10, 4..10: 1-4 %
+    # accepted at (13,9)) to hot (genes 0..5: 11-19 %, 0..1: 35 %), arenas with 1-, 2- and 4-word rows, a chain length that
+    # is no multiple of 32 or 96: final lattice, particle list, integers and counters equal the oracle's, and the three
+    # forms agree.
+    lo, hi = gene_range
+    rng = np.random.default_rng(100 + lo * 16 + hi)
+    gs = np.stack([genomes["agg_evolved"], rng.integers(lo, hi, size=48, dtype=np.uint8),
+                   rng.integers(lo, hi, size=48, dtype=np.uint8)])
+    sizes, seeds, steps = [(13, 9), (26, 18), (9, 2), (40, 12)], [11, 12, 13, 14], 250013
+    res = {}
+    for name in ("adaptive", "parallel", "serial"):
+        got, want, cnt = run_pair(ctx, E.AGG, gs, sizes, seeds, E.RNG_FAST, steps=steps, flags=ROUNDS[name])
+        check_equal(ctx, E.AGG, gs, sizes, seeds, got, want, cnt, E.RNG_FAST, steps, flags=ROUNDS[name],
+                    dump_every=1 if name == "adaptive" else 5)
+        res[name] = got
+    for name in ("parallel", "serial"):
+        assert np.array_equal(res["adaptive"]["i0"], res[name]["i0"])
 
 
 @pytest.mark.parametrize("rounds", ["parallel", "serial"])
