@@ -105,6 +105,25 @@ def child(lib, what):
         for nm, fl in (("serial", E.F_ROUNDS_SERIAL), ("parallel", E.F_ROUNDS_PARALLEL), ("adaptive", E.F_ROUNDS_ADAPTIVE)):
             ms, c = timed(E.AGG, ev, [(13, 9)] * 20000, list(range(1, 20001)), fl, steps=200000)
             report("sweep 20000 x (13,9) x 2e5 evolved (%s)" % nm, ms, c)
+    if "evo200" in what:
+        big = np.tile(evo, (4, 1))
+        for nm, fl in (("serial", E.F_ROUNDS_SERIAL), ("adaptive", E.F_ROUNDS_ADAPTIVE)):
+            ms, c = timed(E.AGG, big, tsz, tsd, fl)
+            report("late-generation pop200 (%s)" % nm, ms, c)
+        for nm, fl in (("serial", E.F_ROUNDS_SERIAL), ("adaptive", E.F_ROUNDS_ADAPTIVE)):
+            ms, c = timed(E.AGG, big[:100], tsz, tsd, fl)
+            report("late-generation pop100 (%s)" % nm, ms, c)
+    if "g0" in what:
+        for P in (100, 200):
+            g0 = bench.synthetic_genomes(0, P, 48)
+            for nm, fl in (("parallel", E.F_ROUNDS_PARALLEL), ("adaptive", E.F_ROUNDS_ADAPTIVE)):
+                ms, c = timed(E.AGG, g0, tsz, tsd, fl)
+                report("generation-0 pop%d (%s)" % (P, nm), ms, c)
+    if "vsweep" in what:
+        ev = np.asarray(bench.EVOLVED_AGG, dtype=np.uint8).reshape(1, 48)
+        for nm, fl in (("serial", E.F_ROUNDS_SERIAL), ("parallel", E.F_ROUNDS_PARALLEL)):
+            ms, c = timed(E.AGG, ev, [(13, 9)] * 20000, list(range(1, 20001)), fl, steps=100000, mode=E.RNG_VERIFY)
+            report("verify sweep 20000 x (13,9) x 1e5 evolved (%s)" % nm, ms, c)
     if "verify" in what:
         ms, c = timed(E.AGG, gs, tsz, tsd, E.F_ROUNDS_PARALLEL, mode=E.RNG_VERIFY, reps=1)
         report("C2 generation verify (parallel)", ms, c)
