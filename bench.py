@@ -432,7 +432,8 @@ def main():
                 # binds (SM issue) and `measured` what ncu saw on this command.
                 "roofline": {"bound": "smem", "achieved": achieved, "peak": peak_smem, "unit": "GB/s",
                              "frac": achieved / peak_smem, "traffic": traffic,
-                             "kernel": "sops_chain_kernel<AGG,RW=1,%s,parallel rounds>" % args.rng, "kernel_ms": k_ms,
+                             "kernel": "sops_chain_kernel<AGG,RW=1,%s,%s rounds>" % (args.rng, "adaptive" if args.rng == "fast" else "parallel"),
+                             "kernel_ms": k_ms,
                              "alg_bytes_per_attempt": alg_bytes, "p_poss": p_poss, "p_acc": p_acc,
                              "peak_source": "%s sm_max_mhz x 148 SMs x 128 B/clk shared memory" % peak_src,
                              "binding": {"ceiling": "SM issue (thread-instructions)", "frac": issue["frac"], **issue},

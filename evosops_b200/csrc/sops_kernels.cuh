@@ -34,18 +34,34 @@
 
 #include "sops_rng.cuh"
 
-// ROUNDS_ADAPTIVE: batches evaluated side by side while a chain is calm, and the switching thresholds (see run_instance)
+// ROUNDS_ADAPTIVE: batches evaluated side by side while a chain is calm, and the switching thresholds (see run_instance).
+// `ema` is the running mean of commits per 32-step batch x 64.
 #ifndef SOPS_WIDE_N
 #define SOPS_WIDE_N 3
 #endif
 #ifndef SOPS_WIDE_HOT1
-#define SOPS_WIDE_HOT1 6            // calm -> hot: commits in one wide iteration (32 N steps)
+#define SOPS_WIDE_HOT1 6            // aggregation, calm -> hot: commits in one wide iteration (32 N steps) ...
 #endif
 #ifndef SOPS_WIDE_HOT2
 #define SOPS_WIDE_HOT2 9            // ... or in two consecutive wide iterations
 #endif
 #ifndef SOPS_WIDE_CALM
-#define SOPS_WIDE_CALM 16           // hot -> calm: running mean of commits per batch x 16 falls below this
+#define SOPS_WIDE_CALM 64           // aggregation, hot -> calm: ema below this (one commit per batch)
+#endif
+// The other behaviours re-derive through divergent regions when a commit touches a later proposal, so a commit of the
+// side-by-side form costs them more and they leave it earlier; and their parallel rounds carry a higher fixed cost per
+// batch than aggregation's, so between calm and hot they go one batch at a time through the serial rounds.
+#ifndef SOPS_WIDE_HOT1_O
+#define SOPS_WIDE_HOT1_O 3
+#endif
+#ifndef SOPS_WIDE_HOT2_O
+#define SOPS_WIDE_HOT2_O 4
+#endif
+#ifndef SOPS_WIDE_CALM_O
+#define SOPS_WIDE_CALM_O 19         // -> side by side: fewer than 0.3 commits per batch
+#endif
+#ifndef SOPS_WIDE_MID_O
+#define SOPS_WIDE_MID_O 112         // serial <-> parallel rounds: 1.75 commits per batch
 #endif
 
 namespace sops {
@@ -1127,8 +1143,8 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
         // are evaluated side by side against the same lattice — N times the independent work — and resolved in chain order
         // by serial rounds (resolve_batch_wide: a commit repairs every later proposal of all N batches).  The chain
         // switches on its own commit counts: calm -> hot when a wide iteration commits >= SOPS_WIDE_HOT1 times (or two in
-        // a row >= SOPS_WIDE_HOT2), hot -> calm when the running mean of commits per batch (x 16) falls below
-        // SOPS_WIDE_CALM.  Either form retires the sequential chain's steps, so the bits do not depend on the switching.
+        // a row >= SOPS_WIDE_HOT2), hot -> calm when the running mean of commits per batch falls below SOPS_WIDE_CALM / 64.
+        // Either form retires the sequential chain's steps, so the bits do not depend on the switching.
         constexpr bool ADAPT = ROUNDS == ROUNDS_ADAPTIVE;
         constexpr int N = ADAPT ? SOPS_WIDE_N : 1;
         auto narrow_batch = [&]() {
@@ -1141,10 +1157,19 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
             k += R;
         };
         if (ADAPT) {
-            bool calm = false, calm_next = false;
-            uint32_t ema = 2u * SOPS_WIDE_CALM;              // running mean of commits per batch x 16
+            enum { WIDE, ONE_SERIAL, ONE_PARALLEL };
+            constexpr uint32_t HOT1 = BEH == AGG ? SOPS_WIDE_HOT1 : SOPS_WIDE_HOT1_O, HOT2 = BEH == AGG ? SOPS_WIDE_HOT2 : SOPS_WIDE_HOT2_O;
+            constexpr uint32_t CALM = BEH == AGG ? SOPS_WIDE_CALM : SOPS_WIDE_CALM_O;
+            constexpr uint32_t MID = BEH == AGG ? 0u : SOPS_WIDE_MID_O;      // (aggregation has no serial single-batch phase)
+            auto form_of = [&](uint32_t e) -> int {
+                if (e < CALM) return WIDE;
+                if constexpr (BEH != AGG) { if (e < MID) return ONE_SERIAL; }
+                return ONE_PARALLEL;
+            };
+            int form = ONE_PARALLEL, form_next = ONE_PARALLEL;
+            uint32_t ema = 2u * (MID > CALM ? MID : CALM);
             while (k + 32 * N <= steps) {                    // (the chain's last steps go through the plain loop below)
-                if (calm) {
+                if (form == WIDE) {
                     Prop b[N];
                     uint32_t w[N];
                     w[0] = curw;
@@ -1168,21 +1193,35 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
                         for (int i = 0; i < N; ++i) { nposs += b[i].poss ? 1u : 0u; w[i] = nw[i]; }
                         k += 32 * N;
                         const uint32_t c = ncommit - c0;
-                        if (c >= SOPS_WIDE_HOT1 || c + prev >= SOPS_WIDE_HOT2) calm = false;
+                        if (c >= HOT1 || c + prev >= HOT2) form = BEH == AGG ? ONE_PARALLEL : ONE_SERIAL;
                         prev = c;
-                    } while (calm && k + 32 * N <= steps);
+                    } while (form == WIDE && k + 32 * N <= steps);
                     curw = w[0];
-                    calm_next = false;
-                    ema = 2u * SOPS_WIDE_CALM;
+                    form_next = form;
+                    ema = 2u * CALM;
+                } else if (BEH != AGG && form == ONE_SERIAL) {
+                    do {
+                        const uint32_t c0 = ncommit;
+                        const uint32_t nxtw = draw(k + 32 + lane);
+                        unpack(curw, cur);
+                        evaluate<BEH, RW>(L, g, cur);
+                        resolve_batch<BEH, RW, false, ROUNDS_SERIAL>(L, g, lane, true, cur, ncommit);
+                        nposs += cur.poss ? 1u : 0u;
+                        curw = nxtw;
+                        k += 32;
+                        form = form_next;
+                        ema = ema - (ema >> 3) + 8u * (ncommit - c0);
+                        form_next = form_of(ema);
+                    } while (form == ONE_SERIAL && k + 32 * N <= steps);
                 } else {
                     do {
                         const uint32_t c0 = ncommit;
                         narrow_batch();
                         // (the decision lags one batch: the loop branch never waits for this batch's commit count)
-                        calm = calm_next;
-                        ema = ema - (ema >> 3) + 2u * (ncommit - c0);
-                        calm_next = ema < SOPS_WIDE_CALM;
-                    } while (!calm && k + 32 * N <= steps);
+                        form = form_next;
+                        ema = ema - (ema >> 3) + 8u * (ncommit - c0);
+                        form_next = form_of(ema);
+                    } while (form == ONE_PARALLEL && k + 32 * N <= steps);
                 }
             }
         }

@@ -113,6 +113,35 @@ def child(lib, what):
         for nm, fl in (("serial", E.F_ROUNDS_SERIAL), ("adaptive", E.F_ROUNDS_ADAPTIVE)):
             ms, c = timed(E.AGG, big[:100], tsz, tsd, fl)
             report("late-generation pop100 (%s)" % nm, ms, c)
+    if "calm" in what:
+        # calm loco / coat populations (genes 6..10: rarely accepting), one GA generation's shape
+        for lo in (5, 7):
+            glo = np.random.default_rng(40 + lo).integers(lo, 11, size=(50, 144), dtype=np.uint8)
+            lsz, lsd = bench.trial_list([(13, 9)], [1, 2, 3, 4, 5])
+            ori = (np.arange(250) % 3 + 1).astype(np.uint8)
+            for nm, fl in (("parallel", E.F_ROUNDS_PARALLEL), ("serial", E.F_ROUNDS_SERIAL), ("adaptive", E.F_ROUNDS_ADAPTIVE)):
+                ms, c = timed(E.LOCO, glo, lsz, lsd, fl, w=(0.75, 0.25), orient=ori, steps=4000000)
+                report("loco genes %d..10 pop50 (13,9) 4e6 (%s)" % (lo, nm), ms, c)
+            gc = np.random.default_rng(50 + lo).integers(lo, 11, size=(50, 600), dtype=np.uint8)
+            csz, csd = bench.trial_list([(20, 5, 2), (26, 8, 4)], [1, 2, 3, 4, 5])
+            for nm, fl in (("parallel", E.F_ROUNDS_PARALLEL), ("serial", E.F_ROUNDS_SERIAL), ("adaptive", E.F_ROUNDS_ADAPTIVE)):
+                ms, c = timed(E.COAT, gc, csz, csd, fl, w=(0.65, 0.35), steps=4000000)
+                report("coat genes %d..10 pop50 4e6 (%s)" % (lo, nm), ms, c)
+    if "xover2" in what:
+        for beh, nm, size, w, L in ((E.LOCO, "loco", (13, 9), (0.75, 0.25), 144), (E.COAT, "coat", (20, 5, 2), (0.65, 0.35), 600)):
+            rows = []
+            for lo in range(0, 9):
+                for rep in range(2):
+                    g = np.random.default_rng(900 + 10 * lo + rep).integers(lo, 11, size=(1, L), dtype=np.uint8)
+                    ori = np.asarray([1, 2, 3, 1, 2], dtype=np.uint8) if beh == E.LOCO else None
+                    r = []
+                    for fl in (E.F_ROUNDS_PARALLEL, E.F_ROUNDS_SERIAL, E.F_ROUNDS_ADAPTIVE):
+                        ms, c = timed(beh, g, [size] * 5, [1, 2, 3, 4, 5], fl, steps=1000000, w=w, orient=ori)
+                        r.append(ms * 1e-3 * 1.965e9 / 1e6)
+                    rows.append((c["committed"] / c["attempts"], r[0], r[1], r[2]))
+            rows.sort()
+            for pa, cp, cs, ca in rows:
+                print("    %s p_acc=%.4f  cycles/step parallel=%6.1f serial=%6.1f adaptive=%6.1f" % (nm, pa, cp, cs, ca), flush=True)
     if "g0" in what:
         for P in (100, 200):
             g0 = bench.synthetic_genomes(0, P, 48)
