@@ -17,12 +17,22 @@ full() {   # name, launches to skip, command...
   echo "full $name rc=$?"; tail -2 gpurun_out/plain_$name.log | cut -c1-300
   # only the raw metric table travels back (gpurun_out/ is capped at 64 MiB); KEEP_REP=name keeps that one report
   ncu -i gpurun_out/prof_${name}_$TAG.ncu-rep --page raw --csv > gpurun_out/raw_${name}_$TAG.csv 2>/dev/null
+  # per-instruction stall samples of the two aggregation captures (scripts/sass_hot.py condenses them)
+  case $name in c2|evo) ncu -i gpurun_out/prof_${name}_$TAG.ncu-rep --page source --csv --print-source sass > gpurun_out/src_${name}_$TAG.csv 2>/dev/null;; esac
   if [ "${KEEP_REP:-}" != "$name" ]; then rm -f gpurun_out/prof_${name}_$TAG.ncu-rep; fi
 }
 full c2 3 python bench.py --steps 2 --warmup 3 --no-extra
+full evo 2 python scripts/perf_probe.py evo fast
 full sweep 0 python scripts/perf_probe.py c5s fast
 # (chains capped at 4e6 steps, a fifth of a (13,9) chain: the full generations are in the bench line)
 full sep 1 python scripts/c3_probe.py sep cap=4000000
 full loco 1 python scripts/c3_probe.py loco cap=4000000
 full coat 1 python scripts/c3_probe.py coat cap=4000000
+# a real GA run through the C++ CLI (config C2, 60 generations): wall time per generation as the population converges
+if [ -z "${SKIP_GA:-}" ]; then
+  make -C evosops_b200/host -s
+  ( cd /tmp && time /root/repo/evosops_b200/host/evosops -b agg -e ga -p 50 -g 60 --gran 10 -m 0.08 -k "(6,4)" -k "(10,7)" -k "(13,9)" \
+      -s 1 -s 2 -s 3 -s 4 -s 5 --ga-seed 1 --out /tmp/ga_out -v ) > gpurun_out/ga_c2_run_$TAG.log 2>&1
+  echo "ga rc=$?"; grep -c "Wall Time" gpurun_out/ga_c2_run_$TAG.log; grep "Wall Time" gpurun_out/ga_c2_run_$TAG.log | awk 'NR%10==1'
+fi
 ls -la gpurun_out | tail -20

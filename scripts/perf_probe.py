@@ -46,6 +46,17 @@ for mode in modes:
         ctx.launch(); ms = ctx.sync(); ctx.collect(); c = ctx.counters()
         print("sweep evolved 20000 x (13,9) x 2e5 mode=%d ms=%.2f rate=%.3e p_poss=%.3f p_acc=%.4f" % (
             mode, ms, c["attempts"] / ms * 1e3, c["possible"] / c["attempts"], c["committed"] / c["attempts"]), flush=True)
+    if "evo" in which:
+        # bench.py's late-generation population (+-1 mutants of the reference's evolved genome), the C2 batch shape, default form
+        import bench
+        evo = bench.late_generation_population(0, 10)
+        tsz, tsd = bench.trial_list(bench.SIZES_C2, bench.SEEDS_C2)
+        ctx.prepare(E.AGG, evo, tsz, tsd, rng_mode=mode)
+        for _ in range(3):
+            ctx.launch(); ms = ctx.sync()
+        ctx.collect(); c = ctx.counters()
+        print("late-generation population pop50 C2 shape mode=%d ms=%.2f rate=%.3e p_poss=%.3f p_acc=%.4f" % (
+            mode, ms, c["attempts"] / ms * 1e3, c["possible"] / c["attempts"], c["committed"] / c["attempts"]), flush=True)
     if "c5" in which:
         probe("agg (13,9) 20000 inst x 2e5 steps", E.AGG, 1, [(13, 9)], list(range(1, 20001)), mode, steps=200000)
         probe("agg (13,9) 100000 inst x 1e5 steps", E.AGG, 1, [(13, 9)], list(range(1, 100001)), mode, steps=100000)
