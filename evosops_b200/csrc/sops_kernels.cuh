@@ -1147,14 +1147,19 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
         // Either form retires the sequential chain's steps, so the bits do not depend on the switching.
         constexpr bool ADAPT = ROUNDS == ROUNDS_ADAPTIVE;
         constexpr int N = ADAPT ? SOPS_WIDE_N : 1;
-        auto narrow_batch = [&]() {
+        // `room` steps must remain after the batch for the caller's loop to go on: for an uncut batch (the usual case) that test
+        // is made before the batch, off the path from the commit round to the loop branch
+        auto narrow_batch = [&](uint32_t room = 32) -> bool {
+            const bool more_if_full = k + 32 + room <= steps;
             const uint32_t nxtw = draw(k + 32 + lane);
             unpack(curw, cur);
             evaluate<BEH, RW>(L, g, cur);
             const uint32_t R = resolve_batch<BEH, RW, false, ROUNDS>(L, g, lane, true, cur, ncommit);
             nposs += (cur.poss && lane < R) ? 1u : 0u;
-            curw = R == 32 ? nxtw : realign(curw, nxtw, R);
+            if (R == 32) { curw = nxtw; k += 32; return more_if_full; }
+            curw = realign(curw, nxtw, R);
             k += R;
+            return k + room <= steps;
         };
         if (ADAPT) {
             enum { WIDE, ONE_SERIAL, ONE_PARALLEL };
@@ -1214,18 +1219,19 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
                         form_next = form_of(ema);
                     } while (form == ONE_SERIAL && k + 32 * N <= steps);
                 } else {
+                    bool more;
                     do {
                         const uint32_t c0 = ncommit;
-                        narrow_batch();
+                        more = narrow_batch(32 * N);
                         // (the decision lags one batch: the loop branch never waits for this batch's commit count)
                         form = form_next;
                         ema = ema - (ema >> 3) + 8u * (ncommit - c0);
                         form_next = form_of(ema);
-                    } while (form == ONE_PARALLEL && k + 32 * N <= steps);
+                    } while (form == ONE_PARALLEL && more);
                 }
             }
         }
-        while (k + 32 <= steps) narrow_batch();
+        if (k + 32 <= steps) while (narrow_batch()) {}
         while (k < steps) {
             const uint32_t tail = (uint32_t)(steps - k);     // 1..31
             const bool active = lane < tail;
