@@ -20,7 +20,11 @@
 //     point all accepted lanes commit at once (shared-memory atomics).  A lane that proposed a particle an earlier lane
 //     moves cuts the batch (the next batch starts there).  Serial rounds (resolve_batch): the lowest accepted lane
 //     commits, later lanes patch their window arithmetically and only touched lanes re-derive — fewer instructions
-//     when at most one lane of a batch accepts.  ROUNDS is a template parameter; both give the sequential chain's bits.
+//     when at most one lane of a batch accepts.  Adaptive rounds (fast mode; chains with a warp scheduler to themselves):
+//     a chain that rarely commits evaluates THREE batches side by side against the same lattice — the independent work
+//     that fills a lone warp's idle issue slots — and resolves them in chain order by serial rounds (resolve_batch_wide);
+//     every chain switches between the forms on its own commit counts (run_instance).  ROUNDS is a template parameter;
+//     every form gives the sequential chain's bits.
 //   * Aggregation decides through a perfect hash of the 8 neighbourhood cells into a per-instance threshold table.
 //   * Both RNG modes are counter based: fast = Philox2x32-10 keyed per step; verify = the WyRand
 //     double chain, whose draw count per step (2 or 3) depends on the state — resolved per batch by a

@@ -9,7 +9,7 @@ import evosops_b200 as E
 import bench
 
 ctx = E.Context()
-FORMS = [("parallel", E.F_ROUNDS_PARALLEL), ("serial", E.F_ROUNDS_SERIAL)]
+FORMS = [("parallel", E.F_ROUNDS_PARALLEL), ("serial", E.F_ROUNDS_SERIAL), ("adaptive", E.F_ROUNDS_ADAPTIVE)]
 which = sys.argv[1:] or ["c2", "evo", "worst", "sweep"]
 only = [w[5:] for w in which if w.startswith("form=")]
 if only:
