@@ -218,9 +218,8 @@ kernel_fn pick_sep_narrow(int rw, int mode) {
     return mode == 0 ? sops::sops_chain_kernel<sops::SEP, 2, 0, ROUNDS> : sops::sops_chain_kernel<sops::SEP, 2, 1, ROUNDS>;
 }
 // adaptive rounds: aggregation in fast mode only (the one behaviour whose calm chains gain from them)
-// adaptive rounds: fast mode; aggregation, locomotion and coating (separation's calm chains gain nothing from them: every
-// one of its steps is "possible" and its decision is the costly part)
-bool has_adaptive_rounds(int beh, int mode) { return beh != SOPS_SEP && mode == SOPS_RNG_FAST; }
+// adaptive rounds: fast mode; every behaviour (separation: one- and two-word rows, like its parallel rounds)
+bool has_adaptive_rounds(int beh, int mode, int rw) { return mode == SOPS_RNG_FAST && (beh != SOPS_SEP || rw <= 2); }
 template <int BEH>
 kernel_fn pick_adaptive(int rw) {
     if (rw == 1) return sops::sops_chain_kernel<BEH, 1, 1, sops::ROUNDS_ADAPTIVE>;
@@ -229,8 +228,10 @@ kernel_fn pick_adaptive(int rw) {
     return sops::sops_chain_kernel<BEH, 8, 1, sops::ROUNDS_ADAPTIVE>;
 }
 kernel_fn kernel_for(int beh, int rw, int mode, int rounds) {
-    if (rounds == sops::ROUNDS_ADAPTIVE && has_adaptive_rounds(beh, mode))
+    if (rounds == sops::ROUNDS_ADAPTIVE && has_adaptive_rounds(beh, mode, rw)) {
+        if (beh == SOPS_SEP) return rw == 1 ? sops::sops_chain_kernel<sops::SEP, 1, 1, sops::ROUNDS_ADAPTIVE> : sops::sops_chain_kernel<sops::SEP, 2, 1, sops::ROUNDS_ADAPTIVE>;
         return beh == SOPS_LOCO ? pick_adaptive<sops::LOCO>(rw) : beh == SOPS_COAT ? pick_adaptive<sops::COAT>(rw) : pick_adaptive<sops::AGG>(rw);
+    }
     const bool par = rounds != sops::ROUNDS_SERIAL && has_parallel_rounds(beh, rw);
     switch (beh) {
     case SOPS_AGG: return par ? pick_kernel<sops::AGG, sops::ROUNDS_PARALLEL>(rw, mode) : pick_kernel<sops::AGG, sops::ROUNDS_SERIAL>(rw, mode);
@@ -524,14 +525,14 @@ int sops_batch_prepare(sops_ctx* ctx, int behavior, const uint8_t* genomes, uint
             // the predictor (unknown: parallel)
             if (behavior == SOPS_AGG && ctx->last_p_acc[SOPS_AGG] >= 0.0 && ctx->last_p_acc[SOPS_AGG] < 0.02) grp.rounds = sops::ROUNDS_SERIAL;
             // ... and with at most two chains per warp scheduler (a GA generation) each chain picks its form itself
-            // (aggregation, locomotion, coating; fast mode): a late-generation aggregation population of 50 / 100 / 200
+            // (fast mode): a late-generation aggregation population of 50 / 100 / 200
             // runs 40 / 42 / 25 % faster than through the serial form, a generation-0 one as fast as through the parallel
             // form (population 400, four per scheduler: 3-7 % slower)
-            if (has_adaptive_rounds(behavior, rng_mode) && W <= 8u) grp.rounds = sops::ROUNDS_ADAPTIVE;
+            if (has_adaptive_rounds(behavior, rng_mode, grp.rw) && W <= 8u) grp.rounds = sops::ROUNDS_ADAPTIVE;
             if (flags & SOPS_F_ROUNDS_SERIAL) grp.rounds = sops::ROUNDS_SERIAL;
             if ((flags & SOPS_F_ROUNDS_PARALLEL) && has_parallel_rounds(behavior, grp.rw)) grp.rounds = sops::ROUNDS_PARALLEL;
             if (flags & SOPS_F_ROUNDS_ADAPTIVE)
-                grp.rounds = has_adaptive_rounds(behavior, rng_mode) ? sops::ROUNDS_ADAPTIVE
+                grp.rounds = has_adaptive_rounds(behavior, rng_mode, grp.rw) ? sops::ROUNDS_ADAPTIVE
                            : has_parallel_rounds(behavior, grp.rw) ? sops::ROUNDS_PARALLEL : sops::ROUNDS_SERIAL;
             if (grp.cta_w) grp.rounds = sops::ROUNDS_SERIAL;
             layout_group(grp, behavior, max_pg, max_n);

@@ -67,6 +67,12 @@
 #ifndef SOPS_WIDE_MID_O
 #define SOPS_WIDE_MID_O 112         // serial <-> parallel rounds: 1.75 commits per batch
 #endif
+// Separation has the two single-batch phases only (three batches side by side gained 3 % on its calm chains: every one of its
+// steps is "possible" and its decision is ~60 instructions); its serial rounds find a swap partner through the
+// cell -> particle map the parallel rounds keep, and keep it exact
+#ifndef SOPS_WIDE_MID_SEP
+#define SOPS_WIDE_MID_SEP 80          // serial <-> parallel rounds: 1.25 commits per batch
+#endif
 
 namespace sops {
 
@@ -287,7 +293,8 @@ struct Geo {
 struct Lat {
     uint32_t* p0; uint32_t* p1; uint32_t* p2;
     uint16_t* pos; uint16_t* thr; uint16_t* light;
-    uint16_t* tab;                  // AGG: thresholds by [direction][window hash]
+    uint16_t* tab;                  // AGG: thresholds by [direction][window hash].  SEP: cell -> particle map (when kept)
+    bool inv;                       // SEP: the cell -> particle map is kept (parallel / adaptive rounds)
     uint32_t plut;                  // shared-window address of the patch look-up table (per CTA)
     uint4* cmp;                     // this warp's scratch list of accepted moves (32 entries)
     const uint4* dirtab;            // per direction: back5, mid5, front5 masks, delta | tbit << 16
@@ -498,13 +505,18 @@ __device__ __forceinline__ void commit_and_repair(const Lat& L, const Geo& g, ui
         const bool swap = (ttf >> 31) != 0u;                 // warp-uniform (broadcast)
         uint32_t partner = 0xffffffffu;
         if (swap) {
-            // the partner's index: the reference's participants.iter().position scan (separation.rs:302),
-            // here a warp-wide scan of the position list
+            // the partner's index: the reference's participants.iter().position scan (separation.rs:302); from the
+            // cell -> particle map when the kernel keeps one (adaptive rounds), else a warp-wide scan of the position list
             // (every lane scans its strided share with independent loads, one warp reduction at the end)
-            uint32_t found = 0xffffffffu;
+            if (L.inv) {
+                partner = L.tab[inv_index<RW>(tf)];
+                __syncwarp();                                // every lane has read the map before lane f rewrites it
+            } else {
+                uint32_t found = 0xffffffffu;
 #pragma unroll 4
-            for (uint32_t i = lane; i < g.n; i += 32) if (L.pos[i] == tf) found = i;
-            partner = __reduce_min_sync(0xffffffffu, found);
+                for (uint32_t i = lane; i < g.n; i += 32) if (L.pos[i] == tf) found = i;
+                partner = __reduce_min_sync(0xffffffffu, found);
+            }
         }
         // the committing lane updates the two colour planes itself, from its OWN source / target (predicated loads
         // and stores: no broadcast-derived address arithmetic, no "which plane" / "same word" branches)
@@ -519,6 +531,10 @@ __device__ __forceinline__ void commit_and_repair(const Lat& L, const Geo& g, ui
         }
         if (mine) L.pos[p.idx] = (uint16_t)tf;
         if (swap) L.pos[partner] = (uint16_t)sf;
+        if (L.inv && mine) {                                 // keep the map exact for the batches that go through the parallel rounds
+            L.tab[inv_index<RW>(tf)] = (uint16_t)p.idx;
+            if (swap) L.tab[inv_index<RW>(sf)] = (uint16_t)partner;
+        }
     } else {
         if (BEH == LOCO) {                                   // locomotion.rs:344-519, net effect
             const uint32_t auxf = __shfl_sync(0xffffffffu, p.aux, f);
@@ -1150,7 +1166,7 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
         // a row >= SOPS_WIDE_HOT2), hot -> calm when the running mean of commits per batch falls below SOPS_WIDE_CALM / 64.
         // Either form retires the sequential chain's steps, so the bits do not depend on the switching.
         constexpr bool ADAPT = ROUNDS == ROUNDS_ADAPTIVE;
-        constexpr int N = ADAPT ? SOPS_WIDE_N : 1;
+        constexpr int N = (ADAPT && BEH != SEP) ? SOPS_WIDE_N : 1;      // (separation: no side-by-side phase)
         // `room` steps must remain after the batch for the caller's loop to go on: for an uncut batch (the usual case) that test
         // is made before the batch, off the path from the commit round to the loop branch
         auto narrow_batch = [&](uint32_t room = 32) -> bool {
@@ -1168,10 +1184,11 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
         if (ADAPT) {
             enum { WIDE, ONE_SERIAL, ONE_PARALLEL };
             constexpr uint32_t HOT1 = BEH == AGG ? SOPS_WIDE_HOT1 : SOPS_WIDE_HOT1_O, HOT2 = BEH == AGG ? SOPS_WIDE_HOT2 : SOPS_WIDE_HOT2_O;
-            constexpr uint32_t CALM = BEH == AGG ? SOPS_WIDE_CALM : SOPS_WIDE_CALM_O;
-            constexpr uint32_t MID = BEH == AGG ? 0u : SOPS_WIDE_MID_O;      // (aggregation has no serial single-batch phase)
+            constexpr uint32_t CALM = BEH == AGG ? SOPS_WIDE_CALM : BEH == SEP ? 0u : SOPS_WIDE_CALM_O;
+            constexpr uint32_t MID = BEH == AGG ? 0u : BEH == SEP ? SOPS_WIDE_MID_SEP : SOPS_WIDE_MID_O;
+            // (aggregation has no serial single-batch phase, separation no side-by-side phase)
             auto form_of = [&](uint32_t e) -> int {
-                if (e < CALM) return WIDE;
+                if constexpr (BEH != SEP) { if (e < CALM) return WIDE; }
                 if constexpr (BEH != AGG) { if (e < MID) return ONE_SERIAL; }
                 return ONE_PARALLEL;
             };
@@ -1414,6 +1431,7 @@ __global__ void __launch_bounds__(256, (BEH == AGG && ROUNDS != ROUNDS_ADAPTIVE)
     L.thr = reinterpret_cast<uint16_t*>(base + P.off_thr);
     L.light = reinterpret_cast<uint16_t*>(base + P.off_aux);
     L.tab = reinterpret_cast<uint16_t*>(base + P.off_tab);
+    L.inv = P.inv_words != 0u;
     L.dirtab = s_dirtab;
     L.plut = smem_addr(s_plut);
     L.cmp = s_cmp[warp];
@@ -1553,6 +1571,7 @@ __global__ void __launch_bounds__(32 * W) sops_chain_cta_kernel(const KParams P)
     L.thr = reinterpret_cast<uint16_t*>(smem + P.off_thr);
     L.light = reinterpret_cast<uint16_t*>(smem + P.off_aux);
     L.tab = reinterpret_cast<uint16_t*>(smem + P.off_tab);
+    L.inv = false;
     L.dirtab = s_dirtab;
     L.plut = 0;                                              // (the parallel commit rounds are a warp-kernel form)
     L.cmp = nullptr;

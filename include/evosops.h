@@ -71,11 +71,12 @@ enum {
     SOPS_F_ROUNDS_SERIAL = 32,   /* one commit per round, only lanes whose window changed re-derive          */
     SOPS_F_ROUNDS_PARALLEL = 64, /* all accepted lanes of a batch commit at once (fixed-point patch rounds;
                                     separation: arenas up to 29 layers, else serial)                         */
-    SOPS_F_ROUNDS_ADAPTIVE = 128 /* fast mode; aggregation, locomotion, coating: every chain switches on its own
-                                    acceptance rate between the parallel rounds, serial rounds, and serial rounds
-                                    over three batches evaluated side by side (the default for batches that leave
-                                    at most two chains per warp scheduler, i.e. GA generations; where the form does
-                                    not exist the flag falls back to the parallel one)                        */
+    SOPS_F_ROUNDS_ADAPTIVE = 128 /* fast mode: every chain switches on its own acceptance rate between the parallel
+                                    rounds, the serial rounds and (not separation) serial rounds over three batches
+                                    evaluated side by side (the default for batches that leave at most two chains per
+                                    warp scheduler, i.e. GA generations; where the form does not exist — verification
+                                    mode, separation arenas above 29 layers — the flag falls back to the parallel or
+                                    serial one)                                                                  */
 };
 
 /* Create a context over n_dev CUDA devices (device_ids NULL -> devices 0..n_dev-1). */

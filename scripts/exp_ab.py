@@ -127,8 +127,11 @@ def child(lib, what):
             for nm, fl in (("parallel", E.F_ROUNDS_PARALLEL), ("serial", E.F_ROUNDS_SERIAL), ("adaptive", E.F_ROUNDS_ADAPTIVE)):
                 ms, c = timed(E.COAT, gc, csz, csd, fl, w=(0.65, 0.35), steps=4000000)
                 report("coat genes %d..10 pop50 4e6 (%s)" % (lo, nm), ms, c)
-    if "xover2" in what:
-        for beh, nm, size, w, L in ((E.LOCO, "loco", (13, 9), (0.75, 0.25), 144), (E.COAT, "coat", (20, 5, 2), (0.65, 0.35), 600)):
+    if "xover2" in what or "sepx" in what:
+        behs = ((E.LOCO, "loco", (13, 9), (0.75, 0.25), 144), (E.COAT, "coat", (20, 5, 2), (0.65, 0.35), 600))
+        if "sepx" in what:
+            behs = ((E.SEP, "sep", (13, 9), (0.65, 0.35), 600),)
+        for beh, nm, size, w, L in behs:
             rows = []
             for lo in range(0, 9):
                 for rep in range(2):
@@ -159,7 +162,7 @@ def child(lib, what):
     if "sep" in what:
         gsep = np.random.default_rng(3).integers(0, 11, size=(200, 600), dtype=np.uint8)
         ssz, ssd = bench.trial_list([(13, 9)], [1, 2, 3, 4, 5])
-        for nm, fl in (("parallel", E.F_ROUNDS_PARALLEL), ("serial", E.F_ROUNDS_SERIAL)):
+        for nm, fl in (("parallel", E.F_ROUNDS_PARALLEL), ("serial", E.F_ROUNDS_SERIAL), ("default", 0)):
             ms, c = timed(E.SEP, gsep, ssz, ssd, fl, w=(0.65, 0.35), steps=2000000)
             report("sep pop200 x (13,9) x5, 2e6 steps (%s)" % nm, ms, c)
     if "sepevo" in what:
@@ -172,7 +175,7 @@ def child(lib, what):
                 k = int(r6.integers(0, 600))
                 se[g, k] = min(10, max(0, int(se[g, k]) + (1 if r6.integers(0, 2) else -1)))
         ssz, ssd = bench.trial_list([(13, 9)], [1, 2, 3, 4, 5])
-        for nm, fl in (("parallel", E.F_ROUNDS_PARALLEL), ("serial", E.F_ROUNDS_SERIAL)):
+        for nm, fl in (("parallel", E.F_ROUNDS_PARALLEL), ("serial", E.F_ROUNDS_SERIAL), ("default", 0)):
             ms, c = timed(E.SEP, se, ssz, ssd, fl, w=(0.65, 0.35), steps=4000000)
             report("sep evolved pop50 x (13,9) x5, 4e6 steps (%s)" % nm, ms, c)
     if "loco" in what:

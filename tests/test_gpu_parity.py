@@ -165,19 +165,23 @@ def test_agg_adaptive_rounds_switch_between_forms(ctx, genomes, gene_range):
 
 
 @pytest.mark.parametrize("gene_lo", [0, 3, 5, 7])
-@pytest.mark.parametrize("beh", [E.LOCO, E.COAT])
-def test_loco_coat_adaptive_rounds_switch_between_forms(ctx, beh, gene_lo):
+@pytest.mark.parametrize("beh", [E.LOCO, E.COAT, E.SEP])
+def test_loco_coat_sep_adaptive_rounds_switch_between_forms(ctx, beh, gene_lo):
     # Locomotion and coating switch between three forms (side by side / one batch through the serial rounds / one batch
-    # through the parallel rounds): genes gene_lo..10 take a chain from hot (0: 8-25 % accepted) through the serial
-    # band (3, 5: ~0.5-3 %) to calm (7: < 0.3 %).  Bits equal the oracle's and the forced forms'.
+    # through the parallel rounds), separation between the two single-batch ones (its serial rounds then find the swap
+    # partner through the cell -> particle map and keep it exact for the parallel ones): genes gene_lo..10 take a chain
+    # from hot (0: 8-25 % accepted) through the serial band (3, 5: ~0.5-3 %) to calm (7: < 0.3 %).  Bits equal the
+    # oracle's and the forced forms'.
     rng = np.random.default_rng(300 + 10 * beh + gene_lo)
     gs = rng.integers(gene_lo, 11, size=(3, E.GENOME_LEN[beh]), dtype=np.uint8)
     if beh == E.COAT:
         sizes, seeds = [(20, 5, 2), (26, 8, 4), (12, 2, 1), (40, 6, 3)], [21, 22, 23, 24]
+    elif beh == E.SEP:
+        sizes, seeds = [(13, 9), (26, 18), (9, 2), (40, 12), (6, 4)], [21, 22, 23, 24, 25]      # (40,12): serial-only arena
     else:
         sizes, seeds = [(13, 9), (26, 18), (9, 2), (40, 12)], [21, 22, 23, 24]
     orient = (np.arange(3 * 4) % 3 + 1).astype(np.uint8) if beh == E.LOCO else None
-    steps = 250013
+    steps = 250013 if beh != E.SEP else 120013
     res = {}
     for name in ("adaptive", "parallel"):
         got, want, cnt = run_pair(ctx, beh, gs, sizes, seeds, E.RNG_FAST, steps=steps, orient=orient, flags=ROUNDS[name])
@@ -199,7 +203,7 @@ def test_coat_commit_rounds_under_heavy_acceptance(ctx, rng_mode, rounds):
     assert cnt[2] > 0.1 * cnt[0]
 
 
-@pytest.mark.parametrize("rounds", ["parallel", "serial"])
+@pytest.mark.parametrize("rounds", ["parallel", "serial", "adaptive"])
 @pytest.mark.parametrize("rng_mode", [E.RNG_VERIFY, E.RNG_FAST])
 def test_sep_commit_rounds_under_heavy_acceptance(ctx, genomes, rng_mode, rounds):
     # separation with always-accept genomes: nearly every step is a move or a colour swap, so a 32-step batch holds
