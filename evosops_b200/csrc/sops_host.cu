@@ -529,6 +529,12 @@ int sops_batch_prepare(sops_ctx* ctx, int behavior, const uint8_t* genomes, uint
             // runs 40 / 42 / 25 % faster than through the serial form, a generation-0 one as fast as through the parallel
             // form (population 400, four per scheduler: 3-7 % slower)
             if (has_adaptive_rounds(behavior, rng_mode, grp.rw) && W <= 8u) grp.rounds = sops::ROUNDS_ADAPTIVE;
+            // (locomotion, coating, separation: the single-batch loop of their adaptive kernels is 1-2 % slower than the
+            // parallel-rounds kernel's, so a population whose previous batch was hot on average stays with that one;
+            // aggregation's adaptive kernel is the faster one on hot chains too)
+            if (grp.rounds == sops::ROUNDS_ADAPTIVE && behavior != SOPS_AGG && ctx->last_p_acc[behavior] >= 0.06 &&
+                has_parallel_rounds(behavior, grp.rw))
+                grp.rounds = sops::ROUNDS_PARALLEL;
             if (flags & SOPS_F_ROUNDS_SERIAL) grp.rounds = sops::ROUNDS_SERIAL;
             if ((flags & SOPS_F_ROUNDS_PARALLEL) && has_parallel_rounds(behavior, grp.rw)) grp.rounds = sops::ROUNDS_PARALLEL;
             if (flags & SOPS_F_ROUNDS_ADAPTIVE)
