@@ -1,7 +1,10 @@
 """A/B of kernel build variants (compile-time macros) in ONE GPU session.
 usage: exp_ab.py [what ...] -- name=path/to/lib.so ...     (name "base" = the in-tree library)
 Every variant runs in its own process (the library is loaded once per process): a short parity soak against the oracle,
-then device times of the shapes named in `what` (worst, c2, evo, pop400, sweep, verify, sep, coat, loco)."""
+then device times of the shapes named in `what`: worst (the slowest C2 genome), c2, evo / evo200 (late-generation
+populations), g0 (generation-0 populations of 100 / 200), pop400, sweep, verify, vsweep, sep, sepevo, coat, loco, calm (calm
+locomotion / coating populations), xover / xover2 / sepx (per-genome chain time under every round form, by acceptance rate).
+Build the variants with scripts/exp_build.sh (exp/ is git-ignored; the libraries travel with gpurun)."""
 import os
 import subprocess
 import sys
