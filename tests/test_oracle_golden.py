@@ -173,6 +173,17 @@ def test_theory_aggregation_reaches_published_quality(genomes):
     assert 0.88 < np.mean(vals) < 0.95
 
 
+def test_theory_separation_is_near_published_quality(genomes):
+    # authors' dashed line for the theory separation algorithm (Cannon et al. 2019, lambda = 4, gamma = 6): 0.84
+    # (misc_scripts/plotter_single_sep.py:60,92).  A loose anchor — the plot does not record its sizes, seeds or weights;
+    # with the GA's defaults (w1 0.65, w2 0.35) on (13,9) the oracle's full-length chains give 0.81 +- 0.014.
+    seeds = 8
+    ms = (np.arange(1, seeds + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)).reshape(1, seeds)
+    out, _ = O.eval_batch(O.SEP, genomes["sep_theory"], [(13, 9)] * seeds, list(range(1, seeds + 1)), w1=0.65, w2=0.35,
+                          rng_mode=0, move_seeds=ms, prob_table=1)
+    assert 0.77 < float(out["f"].mean()) < 0.88
+
+
 def test_agg_chain_conserves_particles_and_counts(genomes):
     env = O.Env(O.AGG, genomes["agg_evolved"], 10, 7, seed=3)
     env.step(200000)
