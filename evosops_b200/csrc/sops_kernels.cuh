@@ -84,6 +84,24 @@ enum { MODE_VERIFY = 0, MODE_FAST = 1 };
 // acceptance rate, between the parallel rounds and serial rounds over SOPS_WIDE_N batches evaluated side by side
 enum { ROUNDS_PARALLEL = 0, ROUNDS_SERIAL = 1, ROUNDS_ADAPTIVE = 2 };
 
+// --- the adaptive rounds' controller (run_instance): which form the next batch of a chain takes ----------------------
+// `ema` = running mean of commits per 32-step batch in 1/64 (decay 1/8 per batch; it bottoms out at 7/64 when nothing
+// commits, below every threshold).  Aggregation has no serial single-batch phase, separation no side-by-side phase.
+enum { FORM_WIDE = 0, FORM_ONE_SERIAL = 1, FORM_ONE_PARALLEL = 2 };
+__host__ __device__ constexpr uint32_t adapt_ema_next(uint32_t ema, uint32_t commits) { return ema - (ema >> 3) + 8u * commits; }
+// side by side -> single batches: commits in one wide iteration, or in two consecutive ones
+__host__ __device__ constexpr uint32_t adapt_hot1(int beh) { return beh == 0 ? SOPS_WIDE_HOT1 : SOPS_WIDE_HOT1_O; }
+__host__ __device__ constexpr uint32_t adapt_hot2(int beh) { return beh == 0 ? SOPS_WIDE_HOT2 : SOPS_WIDE_HOT2_O; }
+// ema below calm: side by side; below mid: single batches through the serial rounds; else the parallel rounds
+__host__ __device__ constexpr uint32_t adapt_calm(int beh) { return beh == 0 ? SOPS_WIDE_CALM : beh == 1 ? 0u : SOPS_WIDE_CALM_O; }
+__host__ __device__ constexpr uint32_t adapt_mid(int beh) { return beh == 0 ? 0u : beh == 1 ? SOPS_WIDE_MID_SEP : SOPS_WIDE_MID_O; }
+template <int BEH>
+__host__ __device__ constexpr int adapt_form(uint32_t ema) {
+    if constexpr (adapt_calm(BEH) != 0u) { if (ema < adapt_calm(BEH)) return FORM_WIDE; }
+    if constexpr (adapt_mid(BEH) != 0u) { if (ema < adapt_mid(BEH)) return FORM_ONE_SERIAL; }
+    return FORM_ONE_PARALLEL;
+}
+
 struct Instance {                   // 40 bytes, built on the host, sorted by cost (longest first)
     uint64_t seed;                  // init seed (StdRng::seed_from_u64)
     uint64_t move_seed;
@@ -1182,16 +1200,9 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
             return k + room <= steps;
         };
         if (ADAPT) {
-            enum { WIDE, ONE_SERIAL, ONE_PARALLEL };
-            constexpr uint32_t HOT1 = BEH == AGG ? SOPS_WIDE_HOT1 : SOPS_WIDE_HOT1_O, HOT2 = BEH == AGG ? SOPS_WIDE_HOT2 : SOPS_WIDE_HOT2_O;
-            constexpr uint32_t CALM = BEH == AGG ? SOPS_WIDE_CALM : BEH == SEP ? 0u : SOPS_WIDE_CALM_O;
-            constexpr uint32_t MID = BEH == AGG ? 0u : BEH == SEP ? SOPS_WIDE_MID_SEP : SOPS_WIDE_MID_O;
-            // (aggregation has no serial single-batch phase, separation no side-by-side phase)
-            auto form_of = [&](uint32_t e) -> int {
-                if constexpr (BEH != SEP) { if (e < CALM) return WIDE; }
-                if constexpr (BEH != AGG) { if (e < MID) return ONE_SERIAL; }
-                return ONE_PARALLEL;
-            };
+            constexpr int WIDE = FORM_WIDE, ONE_SERIAL = FORM_ONE_SERIAL, ONE_PARALLEL = FORM_ONE_PARALLEL;
+            constexpr uint32_t HOT1 = adapt_hot1(BEH), HOT2 = adapt_hot2(BEH), CALM = adapt_calm(BEH), MID = adapt_mid(BEH);
+            auto form_of = [&](uint32_t e) -> int { return adapt_form<BEH>(e); };
             int form = ONE_PARALLEL, form_next = ONE_PARALLEL;
             uint32_t ema = 2u * (MID > CALM ? MID : CALM);
             while (k + 32 * N <= steps) {                    // (the chain's last steps go through the plain loop below)
@@ -1236,7 +1247,7 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
                         curw = nxtw;
                         k += 32;
                         form = form_next;
-                        ema = ema - (ema >> 3) + 8u * (ncommit - c0);
+                        ema = adapt_ema_next(ema, ncommit - c0);
                         form_next = form_of(ema);
                     } while (form == ONE_SERIAL && k + 32 * N <= steps);
                 } else {
@@ -1246,7 +1257,7 @@ __device__ __forceinline__ void run_instance(const KParams& P, const Lat& L, con
                         more = narrow_batch(32 * N);
                         // (the decision lags one batch: the loop branch never waits for this batch's commit count)
                         form = form_next;
-                        ema = ema - (ema >> 3) + 8u * (ncommit - c0);
+                        ema = adapt_ema_next(ema, ncommit - c0);
                         form_next = form_of(ema);
                     } while (form == ONE_PARALLEL && more);
                 }

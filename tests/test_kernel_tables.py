@@ -92,3 +92,32 @@ def test_patch_lookup_table_and_index_arithmetic(tables):
             if tgt == (0, 0):
                 want |= 1 << 30
         assert word == want, (orow, ocol, d, lane_f, lane_l, hex(word), hex(want))
+
+
+def test_adaptive_rounds_controller(tables):
+    # The adaptive kernels pick a chain's round form from a running mean of its commits per 32-step batch (in 1/64, decay
+    # 1/8).  With a constant commit count c the mean settles at ~64 c; with none it must fall below every "calm" threshold
+    # (integer decay stops at 7/64: a threshold at or below that would never be crossed — a bug this test pins); the forms
+    # are ordered side by side < serial single batches < parallel rounds in commit rate; aggregation has no serial
+    # single-batch phase, separation no side-by-side phase; and a chain that leaves the side-by-side phase (hot1 commits
+    # in one iteration of wide_n batches, or hot2 in two) commits more per batch than the rate that brought it there.
+    WIDE, ONE_SERIAL, ONE_PARALLEL = 0, 1, 2
+    AGG, SEP = 0, 1
+    for a in tables["adapt"]:
+        steady = {c: (ema, form) for c, ema, form in a["steady"]}
+        for c, (ema, _) in steady.items():
+            assert abs(ema - 64 * c) <= 7, (a["beh"], c, ema)
+        assert steady[0][0] <= 7
+        if a["beh"] == SEP:
+            assert a["calm"] == 0 and all(form != WIDE for _, form in steady.values())
+            assert steady[0][1] == ONE_SERIAL
+        else:
+            assert a["calm"] > 7 and steady[0][1] == WIDE
+            # leaving the side-by-side phase needs a higher commit rate than entering it
+            assert a["hot1"] / a["wide_n"] > a["calm"] / 64.0 and a["hot2"] / (2 * a["wide_n"]) > a["calm"] / 64.0
+        if a["beh"] == AGG:
+            assert a["mid"] == 0 and all(form != ONE_SERIAL for _, form in steady.values())
+        else:
+            assert a["mid"] > a["calm"]
+        forms = [steady[c][1] for c in sorted(steady)]
+        assert forms == sorted(forms) and forms[-1] == ONE_PARALLEL      # monotone in the commit rate, hot chains: parallel rounds

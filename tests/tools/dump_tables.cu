@@ -50,6 +50,20 @@ int main() {
                     std::printf("%s[%d, %d, %d, %u, %u, %u]", first ? "" : ", ", orow, ocol, d, lane_f, lane_l, word);
                     first = false;
                 }
+    std::printf("], \"adapt\": [");
+    // The adaptive rounds' controller (adapt_* in the header): thresholds per behaviour, the running mean's fixed points
+    // under a constant commit count per batch (from a hot start, 400 batches), and the form picked there.
+    for (int beh = 0; beh < 4; ++beh) {
+        std::printf("%s{\"beh\": %d, \"hot1\": %u, \"hot2\": %u, \"calm\": %u, \"mid\": %u, \"wide_n\": %d, \"steady\": [",
+                    beh ? ", " : "", beh, adapt_hot1(beh), adapt_hot2(beh), adapt_calm(beh), adapt_mid(beh), SOPS_WIDE_N);
+        for (uint32_t c = 0; c <= 8; ++c) {
+            uint32_t ema = 4096;
+            for (int b = 0; b < 400; ++b) ema = adapt_ema_next(ema, c);
+            const int form = beh == 0 ? adapt_form<0>(ema) : beh == 1 ? adapt_form<1>(ema) : beh == 2 ? adapt_form<2>(ema) : adapt_form<3>(ema);
+            std::printf("%s[%u, %u, %d]", c ? ", " : "", c, ema, form);
+        }
+        std::printf("]}");
+    }
     std::printf("]}\n");
     return 0;
 }
