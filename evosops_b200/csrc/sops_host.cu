@@ -209,7 +209,7 @@ kernel_fn kernel_for_cta(int beh, int rw) {
     default: return rw == 1 ? sops::sops_chain_cta_kernel<sops::LOCO, 1, 4> : sops::sops_chain_cta_kernel<sops::LOCO, 2, 4>;
     }
 }
-// rounds: sops::ROUNDS_PARALLEL (aggregation, coating) or sops::ROUNDS_SERIAL (every behaviour)
+// rounds: sops::ROUNDS_PARALLEL or sops::ROUNDS_SERIAL (every behaviour), sops::ROUNDS_ADAPTIVE (fast mode)
 // (separation keeps a cell -> particle map for it: one- and two-word rows only, 2 or 6 KB per chain)
 bool has_parallel_rounds(int beh, int rw) { return beh != SOPS_SEP || rw <= 2; }
 template <int ROUNDS>

@@ -78,7 +78,7 @@ namespace sops {
 
 enum { AGG = 0, SEP = 1, COAT = 2, LOCO = 3 };
 enum { MODE_VERIFY = 0, MODE_FAST = 1 };
-// commit-round form of the warp kernel: all accepted lanes at once (fixed-point patch rounds; aggregation, coating) or
+// commit-round form of the warp kernel: all accepted lanes at once (fixed-point patch rounds) or
 // one commit per round with re-derivation of the lanes whose window changed (every behaviour)
 // ROUNDS_ADAPTIVE (fast mode, chains that have a warp scheduler to themselves): every chain switches, on its own running
 // acceptance rate, between the parallel rounds and serial rounds over SOPS_WIDE_N batches evaluated side by side
@@ -667,7 +667,7 @@ __device__ __forceinline__ void commit_and_repair(const Lat& L, const Geo& g, ui
     commit_and_repair<BEH, RW, 0>(L, g, lane, f, sf, ttf, active, p, nullptr);
 }
 
-// --- parallel commit rounds (aggregation, coating) --------------------------------------------------------------
+// --- parallel commit rounds (aggregation, coating, locomotion; separation below) ----------------------------------
 // The sequential chain asks, for lane l:  decision_l = g(window_l(S0) ^ XOR of the moves of the ACCEPTED lanes f < l).
 // That is a fixed point of a strictly lower-triangular map over the 32 lanes, solved by iteration instead of one
 // commit after the other:
