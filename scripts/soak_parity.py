@@ -32,7 +32,7 @@ for case in range(n_cases):
     steps = int(rng.integers(1, 60000))
     rng_mode = int(rng.integers(0, 2))
     kflag = E.F_FORCE_CTA if (rng_mode == E.RNG_FAST and a <= 29 and rng.integers(0, 4) == 0) else 0
-    kflag |= int(rng.choice([0, E.F_ROUNDS_SERIAL, E.F_ROUNDS_PARALLEL]))
+    kflag |= int(rng.choice([0, E.F_ROUNDS_SERIAL, E.F_ROUNDS_PARALLEL, E.F_ROUNDS_ADAPTIVE]))
     got, want, cnt = run_pair(ctx, beh, gs, [size, size], seeds, rng_mode, steps=steps, move_seeds=ms, orient=orient, flags=kflag)
     check_equal(ctx, beh, gs, [size, size], seeds, got, want, cnt, rng_mode, steps, move_seeds=ms, orient=orient, flags=kflag)
     done += 1
